@@ -1,0 +1,178 @@
+/*
+ * rtdd.h -- C ABI of librtdd.so, the B200 (sm_100a) implementation of the
+ * RealTimeDepthDiffusion hot path.
+ *
+ * This is the drop-in boundary: plain C, plain pointers and sizes, explicit
+ * context handle, int status returns.  Each entry point names the reference
+ * interface it replaces (paths relative to the reference repository).  The
+ * reference-named C++ functions of include/GPUSolver.h, GPUImageProcessing.h and
+ * GPUDepthEffect.h are thin shims over these (csrc/shims.cpp) that keep the
+ * reference's "void + print + continue" error convention and one process-global
+ * context.
+ *
+ * Unless a parameter says "host", every image pointer is a DEVICE pointer owned
+ * by the caller and every pitch is in BYTES, exactly as the reference passes
+ * cv::cuda::GpuMat::ptr()/step.  All work is enqueued on the context's stream
+ * (rtdd_set_stream; default: a blocking stream, which orders itself against the
+ * legacy default stream the way the reference's default-stream launches do).
+ *
+ * Status: 0 = success; > 0 = a cudaError_t value; < 0 = RTDD_E_* argument/state
+ * error.  rtdd_last_error(ctx) returns a printable description of the last
+ * non-zero status.  There is no CPU fallback anywhere behind this interface.
+ */
+#ifndef RTDD_H
+#define RTDD_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RTDD_E_ARG     (-1)   /* bad argument (null pointer, level out of range, size mismatch) */
+#define RTDD_E_STATE   (-2)   /* call-order violation (e.g. solve before rtdd_load_weights) */
+#define RTDD_E_NOMEM   (-3)   /* host allocation failed */
+#define RTDD_E_PEER    (-4)   /* multi-GPU strip set-up failed (no peer access, bad rank layout) */
+
+typedef struct rtdd_ctx rtdd_ctx;
+
+/* ---- life cycle ---------------------------------------------------------- */
+
+/* replaces GPUAllocateDeviceMemory(rows, cols, levels)   ref: include/GPUSolver.h:6, src/GPUSolver.cu:33-54
+ * One context per GPU; scratch planes for levels l = 0..levels-1 of size
+ * floor(rows/2^l) x floor(cols/2^l) in a single HBM arena.  device < 0 = current device. */
+int rtdd_create(int rows, int cols, int levels, int device, rtdd_ctx **out);
+/* replaces GPUFreeDeviceMemory(levels)                    ref: include/GPUSolver.h:7, src/GPUSolver.cu:56-71 */
+int rtdd_destroy(rtdd_ctx *ctx);
+/* replaces GPULoadWeights(beta)                           ref: include/GPUSolver.h:8, src/GPUSolver.cu:264-272 */
+int rtdd_load_weights(rtdd_ctx *ctx, float beta);
+/* stream = a cudaStream_t (NULL restores the context's own stream). */
+int rtdd_set_stream(rtdd_ctx *ctx, void *stream);
+/* replaces the cudaThreadSynchronize in GPUCheckError     ref: src/GPUSolver.cu:21-27 */
+int rtdd_sync(rtdd_ctx *ctx);
+const char *rtdd_last_error(const rtdd_ctx *ctx);
+/* number of kernels this context has launched (directly or through graph replays) since creation */
+unsigned long long rtdd_launch_count(const rtdd_ctx *ctx);
+int rtdd_levels(const rtdd_ctx *ctx);
+/* ref: src/main.cpp:95 -- floor(log2(max(min(cols,rows)/45,1)))+1 */
+int rtdd_pyramid_levels(int rows, int cols);
+/* ref: src/main.cpp:153,263 -- floor(maxIterations / 2^(levels-1-level)) */
+int rtdd_level_iterations(int maxIterations, int levels, int level);
+
+/* ---- the solve ----------------------------------------------------------- */
+
+/* replaces GPUMatrixFreeSolver(depth, depthPitch, scribble, scribblePitch, gray, grayPitch,
+ *                              rows, cols, beta, maxIterations, tolerance, level)
+ * ref: include/GPUSolver.h:9-10, src/GPUSolver.cu:274-316.
+ * One pyramid level: edge-weight pass on (gray, incoming depth), maxIterations
+ * Chebyshev-Jacobi sweeps with scribble (== 255) Dirichlet masking, result back in
+ * `depth` (in place).  beta/tolerance do not exist here because the reference ignores them.
+ * Asynchronous on the context stream (the C++ shim adds the reference's device sync). */
+int rtdd_solve_level(rtdd_ctx *ctx, float *depth, size_t depthPitch,
+                     const uint8_t *scribble, size_t scribblePitch,
+                     const uint8_t *gray, size_t grayPitch,
+                     int rows, int cols, int maxIterations, int level);
+
+/* The edge-weight pass alone (the reference's file-local loadIndexToWeight kernel,
+ * ref: src/GPUSolver.cu:136-224,293), exposed for parity tests and profiling.
+ * Writes the packed link indices of `level` into the context and, if the out pointers
+ * are non-null, copies them to caller DEVICE planes of pitch outPitch bytes:
+ *   linkRight[y][x] = LUT index of the link (x,y)-(x+1,y)   (the reference's `right` of (x,y)
+ *                     == `left` of (x+1,y)); 0 in the last column (no such link)
+ *   linkDown [y][x] = LUT index of the link (x,y)-(x,y+1);   0 in the last row.
+ * Links that leave the image carry weight 0 by position (the reference's index 256). */
+int rtdd_edge_weights(rtdd_ctx *ctx, const float *depth, size_t depthPitch,
+                      const uint8_t *gray, size_t grayPitch,
+                      int rows, int cols, int level,
+                      uint8_t *linkRight, uint8_t *linkDown, size_t outPitch);
+
+/* Device time of the sweep kernels of the most recent rtdd_solve_level on `level` (CUDA events on the
+ * context stream around the sweep launches; excludes the edge-weight pass and the copy back):
+ * the measured counterpart of the reference's per-level `iteration` loop (ref: src/GPUSolver.cu:295-309).
+ * Blocks until that work has finished.  iterations/kernels (may be NULL) return the sweep count and
+ * the number of kernel launches it took. */
+int rtdd_level_sweep_ms(rtdd_ctx *ctx, int level, float *ms, int *iterations, int *kernels);
+
+/* Sweep implementation selector for rtdd_solve_level: 0 = auto (default),
+ * 1 = one sweep per launch, 2 = temporally blocked tiles.  All variants are
+ * bit-identical by construction; the selector exists for tests and profiling. */
+int rtdd_set_sweep_variant(rtdd_ctx *ctx, int variant, int sweepsPerPass);
+
+/* ---- GPUImageProcessing -------------------------------------------------- */
+
+/* replaces GPUConvertToFloat     ref: include/GPUImageProcessing.h:4-5, src/GPUImageProcessing.cu:8-21,72-79 */
+int rtdd_convert_to_float(rtdd_ctx *ctx, const uint8_t *src, size_t srcPitch, float *dst, size_t dstPitch,
+                          const uint8_t *mask, size_t maskPitch, int rows, int cols);
+/* replaces GPUPyrDownAnnotation  ref: include/GPUImageProcessing.h:6-8, src/GPUImageProcessing.cu:23-49,81-91 */
+int rtdd_pyrdown_annotation(rtdd_ctx *ctx, const uint8_t *prevScribble, size_t prevScribblePitch,
+                            const uint8_t *prevEdited, size_t prevEditedPitch, int previousRows, int previousCols,
+                            uint8_t *currScribble, size_t currScribblePitch,
+                            uint8_t *currEdited, size_t currEditedPitch, int currentRows, int currentCols);
+/* replaces GPUPaintImage         ref: include/GPUImageProcessing.h:9-10, src/GPUImageProcessing.cu:51-70,93-100 */
+int rtdd_paint(rtdd_ctx *ctx, int x, int y, int scribbleColor, int scribbleRadius,
+               uint8_t *edited, size_t editedPitch, uint8_t *scribble, size_t scribblePitch, int rows, int cols);
+
+/* ---- GPUDepthEffect ------------------------------------------------------ */
+
+/* replaces GPUSimulateDesaturation  ref: include/GPUDepthEffect.h:6-7, src/GPUDepthEffect.cu:8-27,95-103 */
+int rtdd_desaturate(rtdd_ctx *ctx, const uint8_t *orig, size_t origPitch, const uint8_t *gray, size_t grayPitch,
+                    const float *depth, size_t depthPitch, uint8_t *out, size_t outPitch, int rows, int cols);
+/* replaces GPUSimulateHaze          ref: include/GPUDepthEffect.h:8-9, src/GPUDepthEffect.cu:74-93,115-123 */
+int rtdd_haze(rtdd_ctx *ctx, const uint8_t *orig, size_t origPitch, const float *depth, size_t depthPitch,
+              uint8_t *out, size_t outPitch, int rows, int cols);
+/* replaces GPUSimulateDefocus       ref: include/GPUDepthEffect.h:4-5, src/GPUDepthEffect.cu:29-72,105-113 */
+int rtdd_defocus(rtdd_ctx *ctx, const uint8_t *orig, size_t origPitch, const float *depth, size_t depthPitch,
+                 uint8_t *out, size_t outPitch, int rows, int cols);
+/* All three effects from one read of image + gray + depth (north_star subsystem 3). */
+int rtdd_effects_fused(rtdd_ctx *ctx, const uint8_t *orig, size_t origPitch, const uint8_t *gray, size_t grayPitch,
+                       const float *depth, size_t depthPitch,
+                       uint8_t *desat, size_t desatPitch, uint8_t *haze, size_t hazePitch,
+                       uint8_t *defocus, size_t defocusPitch, int rows, int cols);
+
+/* ---- pyramid ops either side of the path ------------------- */
+
+/* cv::cvtColor(BGR2GRAY)                 ref: src/main.cpp:111,138 */
+int rtdd_bgr2gray(rtdd_ctx *ctx, const uint8_t *bgr, size_t bgrPitch, uint8_t *gray, size_t grayPitch, int rows, int cols);
+/* cv::pyrDown on the u8 gray plane       ref: src/main.cpp:112,143-145,244-246; dst is ceil(rows/2) x ceil(cols/2) */
+int rtdd_pyrdown_gray(rtdd_ctx *ctx, const uint8_t *src, size_t srcPitch, int srcRows, int srcCols,
+                      uint8_t *dst, size_t dstPitch);
+/* cv::pyrUp on the fp32 depth plane      ref: src/main.cpp:272-279; dst is 2n or 2n+1 in each dimension */
+int rtdd_pyrup_depth(rtdd_ctx *ctx, const float *src, size_t srcPitch, int srcRows, int srcCols,
+                     float *dst, size_t dstPitch, int dstRows, int dstCols);
+/* GpuMat::convertTo(CV_8UC1)             ref: src/main.cpp:290 (round half to even, saturate) */
+int rtdd_quantise_u8(rtdd_ctx *ctx, const float *src, size_t srcPitch, uint8_t *dst, size_t dstPitch, int rows, int cols);
+
+/* ---- one whole frame, the body of main.cpp's 'd'/--live branch ------------ */
+
+/* ref: src/main.cpp:232-295.  The context owns device copies of the per-level gray,
+ * scribble, edited and depth planes (what main.cpp keeps in its GpuMat vectors).
+ * rtdd_frame_set_image uploads the level-0 BGR image from HOST memory and builds
+ * the gray pyramid (main.cpp:111-112,138-147); it also resets the depth planes to
+ * 255 and the annotation planes to 0 (main.cpp:130-136). */
+int rtdd_frame_set_image(rtdd_ctx *ctx, const uint8_t *bgrHost, size_t bgrPitch);
+/* One frame: upload level-0 scribble mask + edited image from HOST (main.cpp:236-237),
+ * restrict annotations (:249), inject (:257,281), solve every level coarse to fine
+ * (:261-288) with maxIterations at the coarsest level, quantise (:290) and download the
+ * u8 depth map to HOST (:291).  depthU8Host may be NULL (no download). */
+int rtdd_frame_solve_host(rtdd_ctx *ctx, const uint8_t *scribbleHost, size_t scribblePitch,
+                          const uint8_t *editedHost, size_t editedPitch,
+                          int maxIterations, uint8_t *depthU8Host, size_t depthU8Pitch);
+/* Same frame with the annotation planes already on the device (paint with
+ * rtdd_frame_paint); nothing crosses PCIe. */
+int rtdd_frame_solve(rtdd_ctx *ctx, int maxIterations);
+/* ref: src/main.cpp:46-62 -- brush stroke into the context's level-0 annotation planes */
+int rtdd_frame_paint(rtdd_ctx *ctx, int x, int y, int scribbleColor, int scribbleRadius);
+/* device pointers/pitches of the context-owned planes (for effects, tests, downloads) */
+int rtdd_frame_plane(rtdd_ctx *ctx, int which, int level, void **ptr, size_t *pitch, int *rows, int *cols);
+#define RTDD_PLANE_DEPTH    0   /* fp32 */
+#define RTDD_PLANE_GRAY     1   /* u8, ceil-sized like cv::pyrDown's output */
+#define RTDD_PLANE_SCRIBBLE 2   /* u8 mask, 255 = annotated */
+#define RTDD_PLANE_EDITED   3   /* u8 x 3 */
+#define RTDD_PLANE_BGR      4   /* u8 x 3, level 0 only */
+#define RTDD_PLANE_DEPTH_U8 5   /* u8, level 0 only */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RTDD_H */

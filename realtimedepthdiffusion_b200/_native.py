@@ -1,0 +1,101 @@
+"""ctypes binding of librtdd.so (the C ABI of include/rtdd.h).
+
+There is no fallback: if the shared library has not been built, importing this
+module raises.  Build it with `python -m realtimedepthdiffusion_b200.build` or
+`__graft_entry__.build()`.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "librtdd.so")
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        "librtdd.so is missing (%s): build the CUDA extension first "
+        "(python realtimedepthdiffusion_b200/build.py); there is no CPU fallback" % LIB_PATH)
+
+lib = C.CDLL(LIB_PATH, mode=os.RTLD_LOCAL | os.RTLD_NOW)
+
+vp, sz, i32, f32 = C.c_void_p, C.c_size_t, C.c_int, C.c_float
+
+# name -> (restype, argtypes); every symbol include/rtdd.h declares
+SIGNATURES = {
+    "rtdd_create": (i32, [i32, i32, i32, i32, C.POINTER(vp)]),
+    "rtdd_destroy": (i32, [vp]),
+    "rtdd_load_weights": (i32, [vp, f32]),
+    "rtdd_set_stream": (i32, [vp, vp]),
+    "rtdd_sync": (i32, [vp]),
+    "rtdd_last_error": (C.c_char_p, [vp]),
+    "rtdd_launch_count": (C.c_ulonglong, [vp]),
+    "rtdd_levels": (i32, [vp]),
+    "rtdd_pyramid_levels": (i32, [i32, i32]),
+    "rtdd_level_iterations": (i32, [i32, i32, i32]),
+    "rtdd_solve_level": (i32, [vp, vp, sz, vp, sz, vp, sz, i32, i32, i32, i32]),
+    "rtdd_edge_weights": (i32, [vp, vp, sz, vp, sz, i32, i32, i32, vp, vp, sz]),
+    "rtdd_level_sweep_ms": (i32, [vp, i32, C.POINTER(f32), C.POINTER(i32), C.POINTER(i32)]),
+    "rtdd_set_sweep_variant": (i32, [vp, i32, i32]),
+    "rtdd_convert_to_float": (i32, [vp, vp, sz, vp, sz, vp, sz, i32, i32]),
+    "rtdd_pyrdown_annotation": (i32, [vp, vp, sz, vp, sz, i32, i32, vp, sz, vp, sz, i32, i32]),
+    "rtdd_paint": (i32, [vp, i32, i32, i32, i32, vp, sz, vp, sz, i32, i32]),
+    "rtdd_desaturate": (i32, [vp, vp, sz, vp, sz, vp, sz, vp, sz, i32, i32]),
+    "rtdd_haze": (i32, [vp, vp, sz, vp, sz, vp, sz, i32, i32]),
+    "rtdd_defocus": (i32, [vp, vp, sz, vp, sz, vp, sz, i32, i32]),
+    "rtdd_effects_fused": (i32, [vp, vp, sz, vp, sz, vp, sz, vp, sz, vp, sz, vp, sz, i32, i32]),
+    "rtdd_bgr2gray": (i32, [vp, vp, sz, vp, sz, i32, i32]),
+    "rtdd_pyrdown_gray": (i32, [vp, vp, sz, i32, i32, vp, sz]),
+    "rtdd_pyrup_depth": (i32, [vp, vp, sz, i32, i32, vp, sz, i32, i32]),
+    "rtdd_quantise_u8": (i32, [vp, vp, sz, vp, sz, i32, i32]),
+    "rtdd_frame_set_image": (i32, [vp, vp, sz]),
+    "rtdd_frame_solve_host": (i32, [vp, vp, sz, vp, sz, i32, vp, sz]),
+    "rtdd_frame_solve": (i32, [vp, i32]),
+    "rtdd_frame_paint": (i32, [vp, i32, i32, i32, i32]),
+    "rtdd_frame_plane": (i32, [vp, i32, i32, C.POINTER(vp), C.POINTER(sz), C.POINTER(i32), C.POINTER(i32)]),
+}
+
+# the reference-named C++ shims (Itanium-mangled), same ten functions as include/GPU*.h
+SHIM_SYMBOLS = {
+    "GPUAllocateDeviceMemory": "_Z23GPUAllocateDeviceMemoryiii",
+    "GPUFreeDeviceMemory": "_Z19GPUFreeDeviceMemoryi",
+    "GPULoadWeights": "_Z14GPULoadWeightsf",
+    "GPUMatrixFreeSolver": "_Z19GPUMatrixFreeSolverPfmPhmS0_miififi",
+    "GPUConvertToFloat": "_Z17GPUConvertToFloatPhmPfmS_mii",
+    "GPUPyrDownAnnotation": "_Z20GPUPyrDownAnnotationPhmS_miiS_mS_mii",
+    "GPUPaintImage": "_Z13GPUPaintImageiiiiPhmS_mii",
+    "GPUSimulateDefocus": "_Z18GPUSimulateDefocusPhmPfmS_mii",
+    "GPUSimulateDesaturation": "_Z23GPUSimulateDesaturationPhmS_mPfmS_mii",
+    "GPUSimulateHaze": "_Z15GPUSimulateHazePhmPfmS_mii",
+}
+
+SHIM_SIGNATURES = {
+    "GPUAllocateDeviceMemory": [i32, i32, i32],
+    "GPUFreeDeviceMemory": [i32],
+    "GPULoadWeights": [f32],
+    "GPUMatrixFreeSolver": [vp, sz, vp, sz, vp, sz, i32, i32, f32, i32, f32, i32],
+    "GPUConvertToFloat": [vp, sz, vp, sz, vp, sz, i32, i32],
+    "GPUPyrDownAnnotation": [vp, sz, vp, sz, i32, i32, vp, sz, vp, sz, i32, i32],
+    "GPUPaintImage": [i32, i32, i32, i32, vp, sz, vp, sz, i32, i32],
+    "GPUSimulateDefocus": [vp, sz, vp, sz, vp, sz, i32, i32],
+    "GPUSimulateDesaturation": [vp, sz, vp, sz, vp, sz, vp, sz, i32, i32],
+    "GPUSimulateHaze": [vp, sz, vp, sz, vp, sz, i32, i32],
+}
+
+
+def bind_reference_api(cdll):
+    """Return {name: callable} for the ten reference-named functions of `cdll`
+    (works for librtdd.so's shims and for oracle/_ref/libref.so alike)."""
+    out = {}
+    for name, sym in SHIM_SYMBOLS.items():
+        fn = getattr(cdll, sym)
+        fn.restype = None
+        fn.argtypes = SHIM_SIGNATURES[name]
+        out[name] = fn
+    return out
+
+
+for _name, (_res, _args) in SIGNATURES.items():
+    _fn = getattr(lib, _name)
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+shims = bind_reference_api(lib)

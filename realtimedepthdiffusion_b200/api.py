@@ -1,0 +1,241 @@
+"""Host-side mirror of the reference's operator interface for the hot path.
+
+`DepthDiffusion` wraps one rtdd_ctx (one per GPU).  Method names follow the
+reference's free functions (ref: include/GPUSolver.h:6-10,
+include/GPUImageProcessing.h:4-10, include/GPUDepthEffect.h:4-9): same argument
+meaning, device planes with byte pitches; errors raise RtddError instead of the
+reference's print-and-continue (the C++ shims keep that convention).
+"""
+import ctypes as C
+import math
+
+import torch
+
+from . import _native
+from ._native import lib
+
+
+class RtddError(RuntimeError):
+    pass
+
+
+def pyramid_levels(rows, cols):
+    """ref: src/main.cpp:95"""
+    return int(lib.rtdd_pyramid_levels(rows, cols))
+
+
+def level_iterations(max_iterations, levels, level):
+    """ref: src/main.cpp:263"""
+    return int(lib.rtdd_level_iterations(max_iterations, levels, level))
+
+
+def level_sizes(rows, cols, levels):
+    """Floor sizes of the depth/scribble planes (ref: src/main.cpp:103, src/GPUSolver.cu:42-43)."""
+    return [(int(rows / 2.0 ** l), int(cols / 2.0 ** l)) for l in range(levels)]
+
+
+def pitched_empty(rows, cols, dtype, device, channels=1, align=512, fill=None):
+    """A rows x (cols*channels) plane whose row pitch is a multiple of `align` bytes,
+    like cv::cuda::GpuMat / cudaMallocPitch.  Returns a strided view; .stride(0)*itemsize is the pitch."""
+    item = torch.empty((), dtype=dtype).element_size()
+    row_bytes = cols * channels * item
+    pitch = (row_bytes + align - 1) // align * align
+    if rows == 0 or cols == 0:
+        return torch.empty((rows, cols * channels), dtype=dtype, device=device)
+    base = torch.empty((rows, pitch // item), dtype=dtype, device=device)
+    if fill is not None:
+        base.fill_(fill)
+    return base[:, : cols * channels]
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _pitch(t):
+    if t is None:
+        return 0
+    if t.dim() != 2 or (t.shape[1] > 1 and t.stride(1) != 1):
+        raise ValueError("expected a 2-D plane with unit column stride")
+    return t.stride(0) * t.element_size()
+
+
+class DepthDiffusion:
+    """One solver context on one GPU (replaces GPUAllocateDeviceMemory/GPUFreeDeviceMemory state)."""
+
+    def __init__(self, rows, cols, levels=None, device=None, beta=0.4):
+        if not torch.cuda.is_available():
+            raise RtddError("no CUDA device: this library has no CPU path")
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        self.rows, self.cols = int(rows), int(cols)
+        self.levels = pyramid_levels(rows, cols) if levels is None else int(levels)
+        h = C.c_void_p()
+        rc = lib.rtdd_create(self.rows, self.cols, self.levels, self.device.index, C.byref(h))
+        if rc != 0:
+            raise RtddError("rtdd_create failed with status %d" % rc)
+        self._h = h
+        self.sizes = level_sizes(self.rows, self.cols, self.levels)
+        if beta is not None:
+            self.load_weights(beta)
+
+    # -- plumbing -------------------------------------------------------------
+    def _ck(self, rc):
+        if rc != 0:
+            raise RtddError("%s (status %d)" % (lib.rtdd_last_error(self._h).decode(), rc))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib.rtdd_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        self._ck(lib.rtdd_sync(self._h))
+
+    def set_stream(self, stream):
+        """stream: a torch.cuda.Stream, a raw cudaStream_t int, or None for the context's own stream."""
+        raw = 0 if stream is None else (stream.cuda_stream if hasattr(stream, "cuda_stream") else int(stream))
+        self._ck(lib.rtdd_set_stream(self._h, C.c_void_p(raw)))
+
+    @property
+    def launch_count(self):
+        return int(lib.rtdd_launch_count(self._h))
+
+    def set_sweep_variant(self, variant, sweeps_per_pass=0):
+        self._ck(lib.rtdd_set_sweep_variant(self._h, variant, sweeps_per_pass))
+
+    # -- GPUSolver -------------------------------------------------------------
+    def load_weights(self, beta):
+        self._ck(lib.rtdd_load_weights(self._h, beta))
+
+    def matrix_free_solver(self, depth, scribble, gray, max_iterations, level):
+        """GPUMatrixFreeSolver: one level, `depth` (fp32 plane) updated in place."""
+        rows, cols = depth.shape
+        self._ck(lib.rtdd_solve_level(self._h, _ptr(depth), _pitch(depth), _ptr(scribble), _pitch(scribble),
+                                      _ptr(gray), _pitch(gray), rows, cols, int(max_iterations), int(level)))
+
+    def level_sweep_ms(self, level):
+        """(ms, sweeps, kernel launches) of the most recent solve of `level` (device time, CUDA events)."""
+        ms, it, k = C.c_float(), C.c_int(), C.c_int()
+        self._ck(lib.rtdd_level_sweep_ms(self._h, int(level), C.byref(ms), C.byref(it), C.byref(k)))
+        return ms.value, it.value, k.value
+
+    def edge_weights(self, depth, gray, level):
+        rows, cols = depth.shape
+        right = pitched_empty(rows, cols, torch.uint8, self.device)
+        down = pitched_empty(rows, cols, torch.uint8, self.device)
+        self._ck(lib.rtdd_edge_weights(self._h, _ptr(depth), _pitch(depth), _ptr(gray), _pitch(gray), rows, cols, int(level),
+                                       _ptr(right), _ptr(down), _pitch(right)))
+        return right, down
+
+    # -- GPUImageProcessing ------------------------------------------------------
+    def convert_to_float(self, src, dst, mask):
+        rows, cols = dst.shape
+        self._ck(lib.rtdd_convert_to_float(self._h, _ptr(src), _pitch(src), _ptr(dst), _pitch(dst), _ptr(mask), _pitch(mask), rows, cols))
+
+    def pyrdown_annotation(self, prev_scribble, prev_edited, curr_scribble, curr_edited):
+        pr, pc = prev_scribble.shape
+        cr, cc = curr_scribble.shape
+        self._ck(lib.rtdd_pyrdown_annotation(self._h, _ptr(prev_scribble), _pitch(prev_scribble), _ptr(prev_edited), _pitch(prev_edited), pr, pc,
+                                             _ptr(curr_scribble), _pitch(curr_scribble), _ptr(curr_edited), _pitch(curr_edited), cr, cc))
+
+    def paint_image(self, x, y, color, radius, edited, scribble):
+        rows, cols = scribble.shape
+        self._ck(lib.rtdd_paint(self._h, int(x), int(y), int(color), int(radius), _ptr(edited), _pitch(edited),
+                                _ptr(scribble), _pitch(scribble), rows, cols))
+
+    # -- GPUDepthEffect ----------------------------------------------------------
+    def simulate_desaturation(self, orig, gray, depth, out):
+        rows, cols = depth.shape
+        self._ck(lib.rtdd_desaturate(self._h, _ptr(orig), _pitch(orig), _ptr(gray), _pitch(gray), _ptr(depth), _pitch(depth),
+                                     _ptr(out), _pitch(out), rows, cols))
+
+    def simulate_haze(self, orig, depth, out):
+        rows, cols = depth.shape
+        self._ck(lib.rtdd_haze(self._h, _ptr(orig), _pitch(orig), _ptr(depth), _pitch(depth), _ptr(out), _pitch(out), rows, cols))
+
+    def simulate_defocus(self, orig, depth, out):
+        rows, cols = depth.shape
+        self._ck(lib.rtdd_defocus(self._h, _ptr(orig), _pitch(orig), _ptr(depth), _pitch(depth), _ptr(out), _pitch(out), rows, cols))
+
+    def effects_fused(self, orig, gray, depth, desat, haze, defocus):
+        rows, cols = depth.shape
+        self._ck(lib.rtdd_effects_fused(self._h, _ptr(orig), _pitch(orig), _ptr(gray), _pitch(gray), _ptr(depth), _pitch(depth),
+                                        _ptr(desat), _pitch(desat), _ptr(haze), _pitch(haze), _ptr(defocus), _pitch(defocus), rows, cols))
+
+    # -- pyramid ops ---------------------------------------------------------------
+    def bgr2gray(self, bgr, gray):
+        rows, cols = gray.shape
+        self._ck(lib.rtdd_bgr2gray(self._h, _ptr(bgr), _pitch(bgr), _ptr(gray), _pitch(gray), rows, cols))
+
+    def pyrdown_gray(self, src, dst):
+        rows, cols = src.shape
+        assert dst.shape == ((rows + 1) // 2, (cols + 1) // 2)
+        self._ck(lib.rtdd_pyrdown_gray(self._h, _ptr(src), _pitch(src), rows, cols, _ptr(dst), _pitch(dst)))
+
+    def pyrup_depth(self, src, dst):
+        self._ck(lib.rtdd_pyrup_depth(self._h, _ptr(src), _pitch(src), src.shape[0], src.shape[1], _ptr(dst), _pitch(dst), dst.shape[0], dst.shape[1]))
+
+    def quantise_u8(self, src, dst):
+        rows, cols = src.shape
+        self._ck(lib.rtdd_quantise_u8(self._h, _ptr(src), _pitch(src), _ptr(dst), _pitch(dst), rows, cols))
+
+    # -- whole frame (main.cpp:232-295) -----------------------------------------------
+    def frame_set_image(self, bgr_host):
+        """bgr_host: uint8 numpy array or CPU tensor, rows x cols x 3, C-contiguous."""
+        t = torch.as_tensor(bgr_host)
+        assert t.dtype == torch.uint8 and tuple(t.shape) == (self.rows, self.cols, 3) and t.is_contiguous()
+        self._keep_bgr = t
+        self._ck(lib.rtdd_frame_set_image(self._h, C.c_void_p(t.data_ptr()), self.cols * 3))
+        self.sync()
+
+    def frame_solve_host(self, scribble_host, edited_host, max_iterations=1000, depth_u8_host=None):
+        s = torch.as_tensor(scribble_host)
+        e = torch.as_tensor(edited_host)
+        assert s.dtype == torch.uint8 and tuple(s.shape) == (self.rows, self.cols) and s.is_contiguous()
+        assert e.dtype == torch.uint8 and tuple(e.shape) == (self.rows, self.cols, 3) and e.is_contiguous()
+        d = depth_u8_host
+        if d is not None:
+            d = torch.as_tensor(d)
+            assert d.dtype == torch.uint8 and tuple(d.shape) == (self.rows, self.cols) and d.is_contiguous()
+        self._ck(lib.rtdd_frame_solve_host(self._h, C.c_void_p(s.data_ptr()), self.cols, C.c_void_p(e.data_ptr()), self.cols * 3,
+                                           int(max_iterations), C.c_void_p(d.data_ptr()) if d is not None else C.c_void_p(0), self.cols))
+        return d
+
+    def frame_solve(self, max_iterations=1000):
+        self._ck(lib.rtdd_frame_solve(self._h, int(max_iterations)))
+
+    def frame_paint(self, x, y, color, radius):
+        self._ck(lib.rtdd_frame_paint(self._h, int(x), int(y), int(color), int(radius)))
+
+    PLANE_DEPTH, PLANE_GRAY, PLANE_SCRIBBLE, PLANE_EDITED, PLANE_BGR, PLANE_DEPTH_U8 = range(6)
+
+    def frame_plane(self, which, level=0):
+        """Copy of a context-owned plane as a dense torch tensor (for tests / downloads)."""
+        p, pitch, r, c = C.c_void_p(), C.c_size_t(), C.c_int(), C.c_int()
+        self._ck(lib.rtdd_frame_plane(self._h, which, level, C.byref(p), C.byref(pitch), C.byref(r), C.byref(c)))
+        dtype = torch.float32 if which == self.PLANE_DEPTH else torch.uint8
+        ch = 3 if which in (self.PLANE_EDITED, self.PLANE_BGR) else 1
+        item = 4 if dtype == torch.float32 else 1
+        out = torch.empty((r.value, c.value * ch), dtype=dtype, device=self.device)
+        self.sync()
+        _cudart_memcpy2d(out, p.value, pitch.value, c.value * ch * item, r.value)
+        return out
+
+
+def _cudart_memcpy2d(dst, src_ptr, src_pitch, width_bytes, rows):
+    """Device-to-device copy of a pitched plane at a raw pointer into the dense tensor `dst`."""
+
+    class _Holder:
+        pass
+
+    h = _Holder()
+    h.__cuda_array_interface__ = {"shape": (src_pitch * rows,), "typestr": "|u1", "data": (src_ptr, False), "version": 2}
+    flat = torch.as_tensor(h, device=dst.device)
+    dst.view(torch.uint8).view(rows, -1).copy_(flat.view(rows, src_pitch)[:, :width_bytes])
+    torch.cuda.synchronize(dst.device)

@@ -1,0 +1,351 @@
+// GPUDepthEffect kernels: desaturation, haze, defocus -- separately or fused into
+// one read of image + gray + depth.
+//
+// Arithmetic contract (from the PTX of the reference):
+//   desaturation: f = div.rn(d, 255); out_c = cvt.rzi(fma(f, gray, (1 - f) * orig_c)) & 0xFF
+//   haze        : t = expf(div.rn(-2 d, 255)); out_c = cvt.rzi(fma(t, orig_c, (1 - t) * 255)) & 0xFF
+//   defocus     : K = (int)(0.025 * (double)sqrtf((float)(rows^2 + cols^2)));
+//                 a = cvt.rzi.s32.f64((double)(K * d) / 255.0); h = a / 2;
+//                 mean of orig over [y-h, y+h) x [x-h, x+h) clipped to the image,
+//                 out_c = cvt.rzi(div.rn(sum_c, count)) & 0xFF; empty window -> copy orig.
+// The reference gathers the window tap by tap (up to 110^2 taps per pixel at 4K) in
+// fp32; those sums are exact integers while count * 255 < 2^24, so an integer
+// summed-area table reproduces them bit for bit with 4 corner reads.  Windows
+// larger than that (only possible beyond ~10K-pixel diagonals) fall back to the
+// reference's raster-order fp32 accumulation to stay bit-exact.
+//
+// ref: src/GPUDepthEffect.cu:8-123.
+
+#include "rtdd_internal.h"
+
+#include <math.h>
+
+namespace rtdd {
+
+__device__ __forceinline__ unsigned int f2u8(float v) { return __float2uint_rz(v) & 0xFFu; }
+
+// ---------------------------------------------------------------------------
+// summed-area table of the BGR image: S[y][x] = sum over rows < y, cols < x,
+// (rows+1) x (cols+1) uint4 {B, G, R, 0}; u32 wrap-around is harmless because
+// every window sum that is used is < 2^32.
+// Pass A: row prefix sums.  Pass B: column prefix within groups of SAT_G rows.
+// Pass C: exclusive scan of the group totals.  The consumer adds group offsets.
+// ---------------------------------------------------------------------------
+#define SAT_G 64
+
+__global__ void __launch_bounds__(256)
+sat_rows_kernel(const uint8_t *__restrict__ orig, size_t origPitch, uint4 *__restrict__ sat, int rows, int cols)
+{
+    __shared__ uint3 sWarp[8];
+    __shared__ uint3 sCarry;
+    const int y = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int satPitch = cols + 1;
+    uint4 *outRow = sat + (size_t)(y + 1) * satPitch;
+    if (y == 0)
+        for (int x = threadIdx.x; x <= cols; x += blockDim.x) sat[x] = make_uint4(0, 0, 0, 0);
+    if (threadIdx.x == 0) { outRow[0] = make_uint4(0, 0, 0, 0); sCarry = make_uint3(0, 0, 0); }
+    __syncthreads();
+    const uint8_t *row = orig + (size_t)y * origPitch;
+    for (int base = 0; base < cols; base += 256 * 4) {
+        const int x0 = base + threadIdx.x * 4;
+        unsigned int b[4], g[4], r[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int x = x0 + i;
+            const bool in = x < cols;
+            b[i] = in ? __ldg(row + 3 * x) : 0u;
+            g[i] = in ? __ldg(row + 3 * x + 1) : 0u;
+            r[i] = in ? __ldg(row + 3 * x + 2) : 0u;
+        }
+#pragma unroll
+        for (int i = 1; i < 4; i++) { b[i] += b[i - 1]; g[i] += g[i - 1]; r[i] += r[i - 1]; }
+        uint3 tot = make_uint3(b[3], g[3], r[3]);
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned int tb = __shfl_up_sync(0xFFFFFFFFu, tot.x, d);
+            const unsigned int tg = __shfl_up_sync(0xFFFFFFFFu, tot.y, d);
+            const unsigned int tr = __shfl_up_sync(0xFFFFFFFFu, tot.z, d);
+            if (lane >= d) { tot.x += tb; tot.y += tg; tot.z += tr; }
+        }
+        if (lane == 31) sWarp[warp] = tot;
+        __syncthreads();
+        uint3 off = sCarry;
+        for (int w = 0; w < warp; w++) { off.x += sWarp[w].x; off.y += sWarp[w].y; off.z += sWarp[w].z; }
+        // exclusive prefix of this thread = inclusive warp scan - own total + offsets
+        off.x += tot.x - b[3]; off.y += tot.y - g[3]; off.z += tot.z - r[3];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int x = x0 + i;
+            if (x < cols) outRow[x + 1] = make_uint4(off.x + b[i], off.y + g[i], off.z + r[i], 0u);
+        }
+        __syncthreads();
+        if (threadIdx.x == 255) { sCarry = make_uint3(off.x + b[3], off.y + g[3], off.z + r[3]); }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(128)
+sat_cols_kernel(uint4 *__restrict__ sat, uint4 *__restrict__ aux, int rows, int cols)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int g = blockIdx.y;
+    if (x > cols) return;
+    const int satPitch = cols + 1;
+    const int yBeg = g * SAT_G + 1;
+    const int yEnd = min(yBeg + SAT_G, rows + 1);
+    uint4 acc = make_uint4(0, 0, 0, 0);
+    for (int y = yBeg; y < yEnd; y++) {
+        uint4 *p = sat + (size_t)y * satPitch + x;
+        const uint4 v = *p;
+        acc.x += v.x; acc.y += v.y; acc.z += v.z;
+        *p = acc;
+    }
+    aux[(size_t)g * satPitch + x] = acc;
+}
+
+__global__ void __launch_bounds__(128)
+sat_aux_kernel(uint4 *__restrict__ aux, int groups, int cols)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x > cols) return;
+    const int satPitch = cols + 1;
+    uint4 acc = make_uint4(0, 0, 0, 0);
+    for (int g = 0; g < groups; g++) {
+        uint4 *p = aux + (size_t)g * satPitch + x;
+        const uint4 v = *p;
+        *p = acc;                         // exclusive: offset to add to rows of group g
+        acc.x += v.x; acc.y += v.y; acc.z += v.z;
+    }
+}
+
+__device__ __forceinline__ uint4 sat_at(const uint4 *__restrict__ sat, const uint4 *__restrict__ aux, int satPitch, int y, int x)
+{
+    if (y == 0) return make_uint4(0, 0, 0, 0);
+    const uint4 a = __ldg(sat + (size_t)y * satPitch + x);
+    const uint4 o = __ldg(aux + (size_t)((y - 1) / SAT_G) * satPitch + x);
+    return make_uint4(a.x + o.x, a.y + o.y, a.z + o.z, 0u);
+}
+
+// ---------------------------------------------------------------------------
+// the per-pixel effect kernel: any subset of {desaturation, haze, defocus} from a
+// single read of orig (3 B) + gray (1 B) + depth (4 B).  One thread = 4 pixels;
+// when every plane is 4-byte aligned (16 for depth) the 12 colour bytes move as
+// three 32-bit words.
+// ---------------------------------------------------------------------------
+template <bool ALIGNED>
+__device__ __forceinline__ void load_bgr4(const uint8_t *__restrict__ p, int n, unsigned int (&c)[4][3])
+{
+    if (ALIGNED && n == 4) {
+        const unsigned int w0 = __ldg((const unsigned int *)p);
+        const unsigned int w1 = __ldg((const unsigned int *)p + 1);
+        const unsigned int w2 = __ldg((const unsigned int *)p + 2);
+        const unsigned int w[3] = {w0, w1, w2};
+#pragma unroll
+        for (int i = 0; i < 12; i++) c[i / 3][i % 3] = (w[i >> 2] >> (8 * (i & 3))) & 0xFFu;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int k = 0; k < 3; k++) c[i][k] = (i < n) ? (unsigned int)__ldg(p + 3 * i + k) : 0u;
+    }
+}
+
+template <bool ALIGNED>
+__device__ __forceinline__ void store_bgr4(uint8_t *__restrict__ p, int n, const unsigned int (&c)[4][3])
+{
+    if (ALIGNED && n == 4) {
+        unsigned int w[3] = {0u, 0u, 0u};
+#pragma unroll
+        for (int i = 0; i < 12; i++) w[i >> 2] |= c[i / 3][i % 3] << (8 * (i & 3));
+        ((unsigned int *)p)[0] = w[0]; ((unsigned int *)p)[1] = w[1]; ((unsigned int *)p)[2] = w[2];
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            if (i < n) { p[3 * i] = (uint8_t)c[i][0]; p[3 * i + 1] = (uint8_t)c[i][1]; p[3 * i + 2] = (uint8_t)c[i][2]; }
+    }
+}
+
+template <bool ALIGNED, bool DESAT, bool HAZE, bool DEFOCUS>
+__global__ void __launch_bounds__(256)
+effects_kernel(const uint8_t *__restrict__ orig, size_t origPitch, const uint8_t *__restrict__ gray, size_t grayPitch,
+               const float *__restrict__ depth, size_t depthPitch,
+               uint8_t *__restrict__ desat, size_t desatPitch, uint8_t *__restrict__ haze, size_t hazePitch,
+               uint8_t *__restrict__ defocus, size_t defocusPitch,
+               const uint4 *__restrict__ sat, const uint4 *__restrict__ aux, int K, int rows, int cols)
+{
+    const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x4 >= cols || y >= rows) return;
+    const int n = min(4, cols - x4);
+
+    unsigned int c[4][3];
+    load_bgr4<ALIGNED>(orig + (size_t)y * origPitch + 3 * x4, n, c);
+    float d[4];
+    {
+        const float *dRow = (const float *)((const char *)depth + (size_t)y * depthPitch) + x4;
+        if (ALIGNED && n == 4) {
+            const float4 v = __ldg((const float4 *)dRow);
+            d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; i++) d[i] = (i < n) ? __ldg(dRow + i) : 0.0f;
+        }
+    }
+
+    if (DESAT) {
+        unsigned int g[4];
+        const uint8_t *gRow = gray + (size_t)y * grayPitch + x4;
+        if (ALIGNED && n == 4) {
+            const unsigned int w = __ldg((const unsigned int *)gRow);
+#pragma unroll
+            for (int i = 0; i < 4; i++) g[i] = (w >> (8 * i)) & 0xFFu;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; i++) g[i] = (i < n) ? (unsigned int)__ldg(gRow + i) : 0u;
+        }
+        unsigned int o[4][3];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const float f = __fdiv_rn(d[i], 255.0f);
+            const float f1 = __fsub_rn(1.0f, f);
+            const float fg = (float)g[i];
+#pragma unroll
+            for (int k = 0; k < 3; k++) o[i][k] = f2u8(__fmaf_rn(f, fg, __fmul_rn(f1, (float)c[i][k])));
+        }
+        store_bgr4<ALIGNED>(desat + (size_t)y * desatPitch + 3 * x4, n, o);
+    }
+
+    if (HAZE) {
+        unsigned int o[4][3];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const float t = expf(__fdiv_rn(__fmul_rn(d[i], -2.0f), 255.0f));
+            const float h = __fmul_rn(__fsub_rn(1.0f, t), 255.0f);
+#pragma unroll
+            for (int k = 0; k < 3; k++) o[i][k] = f2u8(__fmaf_rn(t, (float)c[i][k], h));
+        }
+        store_bgr4<ALIGNED>(haze + (size_t)y * hazePitch + 3 * x4, n, o);
+    }
+
+    if (DEFOCUS) {
+        const int satPitch = cols + 1;
+        unsigned int o[4][3];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int x = x4 + i;
+            const float kd = __fmul_rn((float)K, d[i]);
+            const int a = __double2int_rz(__ddiv_rn((double)kd, 255.0));
+            const int h = a / 2;
+            o[i][0] = c[i][0]; o[i][1] = c[i][1]; o[i][2] = c[i][2];
+            if (i < n && h > 0) {
+                const int x0 = max(x - h, 0), x1 = min(x + h, cols);
+                const int y0 = max(y - h, 0), y1 = min(y + h, rows);
+                // (h > 0 guarantees a non-empty clipped window for an in-image pixel)
+                const int count = (x1 - x0) * (y1 - y0);
+                float sb, sg, sr;
+                if (count <= 65793) {      // count * 255 < 2^24: the reference's fp32 sums are exact integers
+                    const uint4 s11 = sat_at(sat, aux, satPitch, y1, x1);
+                    const uint4 s01 = sat_at(sat, aux, satPitch, y0, x1);
+                    const uint4 s10 = sat_at(sat, aux, satPitch, y1, x0);
+                    const uint4 s00 = sat_at(sat, aux, satPitch, y0, x0);
+                    sb = (float)(s11.x - s01.x - s10.x + s00.x);
+                    sg = (float)(s11.y - s01.y - s10.y + s00.y);
+                    sr = (float)(s11.z - s01.z - s10.z + s00.z);
+                } else {                   // huge window: replay the reference's raster-order fp32 accumulation
+                    sb = 0.0f; sg = 0.0f; sr = 0.0f;
+                    for (int py = y0; py < y1; py++) {
+                        const uint8_t *r = orig + (size_t)py * origPitch;
+                        for (int px = x0; px < x1; px++) {
+                            sb = __fadd_rn(sb, (float)__ldg(r + 3 * px));
+                            sg = __fadd_rn(sg, (float)__ldg(r + 3 * px + 1));
+                            sr = __fadd_rn(sr, (float)__ldg(r + 3 * px + 2));
+                        }
+                    }
+                }
+                const float fc = (float)count;
+                o[i][0] = f2u8(__fdiv_rn(sb, fc));
+                o[i][1] = f2u8(__fdiv_rn(sg, fc));
+                o[i][2] = f2u8(__fdiv_rn(sr, fc));
+            }
+        }
+        store_bgr4<ALIGNED>(defocus + (size_t)y * defocusPitch + 3 * x4, n, o);
+    }
+}
+
+static bool aligned4(const void *p, size_t pitch) { return (((uintptr_t)p | pitch) & 3u) == 0; }
+static bool aligned16(const void *p, size_t pitch) { return (((uintptr_t)p | pitch) & 15u) == 0; }
+
+template <bool DESAT, bool HAZE, bool DEFOCUS>
+static cudaError_t launch_effects(cudaStream_t s, const uint8_t *orig, size_t origPitch, const uint8_t *gray, size_t grayPitch,
+                                  const float *depth, size_t depthPitch, uint8_t *desat, size_t desatPitch,
+                                  uint8_t *haze, size_t hazePitch, uint8_t *defocus, size_t defocusPitch,
+                                  const uint4 *sat, const uint4 *aux, int K, int rows, int cols)
+{
+    bool al = aligned4(orig, origPitch) && aligned16(depth, depthPitch);
+    if (DESAT) al = al && aligned4(gray, grayPitch) && aligned4(desat, desatPitch);
+    if (HAZE) al = al && aligned4(haze, hazePitch);
+    if (DEFOCUS) al = al && aligned4(defocus, defocusPitch);
+    dim3 block(32, 8);
+    dim3 grid(rtdd_div_up(rtdd_div_up(cols, 4), block.x), rtdd_div_up(rows, block.y));
+    if (al)
+        effects_kernel<true, DESAT, HAZE, DEFOCUS><<<grid, block, 0, s>>>(orig, origPitch, gray, grayPitch, depth, depthPitch,
+            desat, desatPitch, haze, hazePitch, defocus, defocusPitch, sat, aux, K, rows, cols);
+    else
+        effects_kernel<false, DESAT, HAZE, DEFOCUS><<<grid, block, 0, s>>>(orig, origPitch, gray, grayPitch, depth, depthPitch,
+            desat, desatPitch, haze, hazePitch, defocus, defocusPitch, sat, aux, K, rows, cols);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_desaturate(cudaStream_t s, const uint8_t *orig, size_t origPitch, const uint8_t *gray, size_t grayPitch,
+                              const float *depth, size_t depthPitch, uint8_t *out, size_t outPitch, int rows, int cols)
+{
+    return launch_effects<true, false, false>(s, orig, origPitch, gray, grayPitch, depth, depthPitch, out, outPitch,
+                                              nullptr, 0, nullptr, 0, nullptr, nullptr, 0, rows, cols);
+}
+
+cudaError_t launch_haze(cudaStream_t s, const uint8_t *orig, size_t origPitch, const float *depth, size_t depthPitch,
+                        uint8_t *out, size_t outPitch, int rows, int cols)
+{
+    return launch_effects<false, true, false>(s, orig, origPitch, nullptr, 0, depth, depthPitch, nullptr, 0,
+                                              out, outPitch, nullptr, 0, nullptr, nullptr, 0, rows, cols);
+}
+
+// ref: src/GPUDepthEffect.cu:42 -- evaluated on the host with the same IEEE sqrtf / fp64 multiply
+int defocus_kernel_size(int rows, int cols)
+{
+    const float s = sqrtf((float)(unsigned int)(rows * rows + cols * cols));
+    return (int)(0.025 * (double)s);
+}
+
+static int sat_groups(int rows) { return rtdd_div_up(rows, SAT_G); }
+
+size_t defocus_scratch_bytes(int rows, int cols)
+{
+    return ((size_t)(rows + 1) + sat_groups(rows)) * (size_t)(cols + 1) * sizeof(uint4);
+}
+
+cudaError_t launch_defocus(cudaStream_t s, void *scratch, const uint8_t *orig, size_t origPitch, const uint8_t *gray, size_t grayPitch,
+                           const float *depth, size_t depthPitch, uint8_t *defocus, size_t defocusPitch,
+                           uint8_t *desat, size_t desatPitch, uint8_t *haze, size_t hazePitch,
+                           int rows, int cols, int *launched)
+{
+    uint4 *sat = (uint4 *)scratch;
+    uint4 *aux = sat + (size_t)(rows + 1) * (cols + 1);
+    const int groups = sat_groups(rows);
+    const int K = defocus_kernel_size(rows, cols);
+    *launched = 0;
+    sat_rows_kernel<<<rows, 256, 0, s>>>(orig, origPitch, sat, rows, cols);
+    sat_cols_kernel<<<dim3(rtdd_div_up(cols + 1, 128), groups), 128, 0, s>>>(sat, aux, rows, cols);
+    sat_aux_kernel<<<rtdd_div_up(cols + 1, 128), 128, 0, s>>>(aux, groups, cols);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    *launched = 4;
+    if (desat && haze)
+        return launch_effects<true, true, true>(s, orig, origPitch, gray, grayPitch, depth, depthPitch, desat, desatPitch,
+                                                haze, hazePitch, defocus, defocusPitch, sat, aux, K, rows, cols);
+    return launch_effects<false, false, true>(s, orig, origPitch, nullptr, 0, depth, depthPitch, nullptr, 0, nullptr, 0,
+                                              defocus, defocusPitch, sat, aux, K, rows, cols);
+}
+
+}  // namespace rtdd

@@ -1,0 +1,680 @@
+// Host side of librtdd.so: contexts, the HBM arena, the per-level sweep schedule
+// (CUDA graphs), and the extern "C" entry points declared in include/rtdd.h.
+//
+// ref: src/GPUSolver.cu:33-71 (alloc/free), :264-272 (LUT), :274-316 (level driver),
+//      src/main.cpp:95,153,232-295 (pyramid orchestration restated by rtdd_frame_*).
+
+#include "rtdd_internal.h"
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+int rtdd_fail(rtdd_ctx *ctx, int code, const char *where)
+{
+    if (ctx) {
+        char buf[256];
+        if (code > 0)
+            snprintf(buf, sizeof buf, "%s: %s", where, cudaGetErrorString((cudaError_t)code));
+        else
+            snprintf(buf, sizeof buf, "%s: %s", where,
+                     code == RTDD_E_ARG ? "bad argument" : code == RTDD_E_STATE ? "call-order violation"
+                     : code == RTDD_E_NOMEM ? "host allocation failed" : code == RTDD_E_PEER ? "peer set-up failed" : "error");
+        ctx->err = buf;
+    }
+    return code;
+}
+
+int rtdd_check(rtdd_ctx *ctx, cudaError_t e, const char *where)
+{
+    if (e == cudaSuccess) return 0;
+    return rtdd_fail(ctx, (int)e, where);
+}
+
+#define RTDD_TRY(expr, where)                                   \
+    do {                                                        \
+        const int _rc = rtdd_check(ctx, (expr), (where));       \
+        if (_rc) return _rc;                                    \
+    } while (0)
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+// ref: src/GPUSolver.cu:282-285,297-299 -- rho*rho in fp32, the quotient in fp64, stored to fp32.
+void omega_schedule(int iterations, std::vector<float> &om)
+{
+    const int S = 10;
+    const float rho = 0.99f;
+    float omega = 0.0f;
+    om.resize(iterations > 0 ? iterations : 0);
+    for (int it = 0; it < iterations; it++) {
+        if (it < S) omega = 1.0f;
+        else if (it == S) { const float r2 = rho * rho; omega = (float)(2.0 / (2.0 - (double)r2)); }
+        else { const float r2 = rho * rho; const float r2w = r2 * omega; omega = (float)(4.0 / (4.0 - (double)r2w)); }
+        om[it] = omega;
+    }
+}
+
+void destroy_graphs(rtdd_ctx *ctx)
+{
+    for (auto &kv : ctx->graphs)
+        if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    ctx->graphs.clear();
+}
+
+// Sweep-variant policy (all variants are bit-identical; this only decides speed).
+void pick_variant(const rtdd_ctx *ctx, const RtddLevel &L, int iters, int *variant, int *T)
+{
+    int v = ctx->variant, t = ctx->sweepsPerPass;
+    if (v == 0) v = 2;
+    if (v == 2) {
+        if (t <= 0) {
+            const long px = (long)L.rows * L.cols;
+            t = (px >= (1L << 20)) ? 8 : 12;
+        }
+        if (t > RTDD_MAX_T) t = RTDD_MAX_T;
+        if (t > iters) t = iters > 0 ? iters : 1;
+    } else {
+        t = 1;
+    }
+    *variant = v;
+    *T = t;
+}
+
+// Build (or fetch) the CUDA graph that runs `iters` sweeps on level `level`
+// starting from plane x[0] (prev = implicit zeros).
+int get_sweep_graph(rtdd_ctx *ctx, int level, int iters, RtddGraph **out)
+{
+    const RtddLevel &L = ctx->lv[level];
+    int variant, T;
+    pick_variant(ctx, L, iters, &variant, &T);
+    const RtddGraphKey key{level, iters, variant, T};
+    auto it = ctx->graphs.find(key);
+    if (it != ctx->graphs.end()) { *out = &it->second; return 0; }
+
+    std::vector<float> om;
+    omega_schedule(iters, om);
+    const float gamma = 0.99f;
+
+    RtddGraph g;
+    cudaGraph_t graph = nullptr;
+    cudaStream_t cs = ctx->captureStream;
+    RTDD_TRY(cudaStreamBeginCapture(cs, cudaStreamCaptureModeRelaxed), "cudaStreamBeginCapture");
+    cudaError_t e = cudaSuccess;
+    int kernels = 0, result = 0;
+    if (variant == 1) {
+        // three-plane rotation: x_k in plane k%3, x_{k+1} -> (k+1)%3, x_{k-1} in (k+2)%3
+        for (int k = 0; k < iters && e == cudaSuccess; k++) {
+            e = rtdd::launch_sweep_single(cs, L, ctx->dLut, L.x[k % 3], L.x[(k + 2) % 3], L.x[(k + 1) % 3], om[k], gamma, k == 0);
+            kernels++;
+        }
+        result = iters % 3;
+    } else {
+        // pair A = planes (0,1), pair B = planes (2,3); each pass reads one pair and writes the other
+        int cur = 0;
+        for (int k = 0; k < iters && e == cudaSuccess; k += T) {
+            const int n = (iters - k < T) ? iters - k : T;
+            rtdd::OmegaPack pack;
+            for (int i = 0; i < RTDD_MAX_T; i++) pack.w[i] = (i < n) ? om[k + i] : 0.0f;
+            const int src = cur, dst = cur ^ 2;
+            e = rtdd::launch_sweep_blocked(cs, L, ctx->dLut, L.x[src], L.x[src + 1], L.x[dst], L.x[dst + 1], pack, T, n, gamma,
+                                           k == 0, ctx->smCount);
+            kernels++;
+            cur = dst;
+        }
+        result = cur;
+    }
+    cudaError_t e2 = cudaStreamEndCapture(cs, &graph);
+    if (e != cudaSuccess) { if (graph) cudaGraphDestroy(graph); return rtdd_check(ctx, e, "sweep capture"); }
+    RTDD_TRY(e2, "cudaStreamEndCapture");
+    cudaGraphExec_t exec = nullptr;
+    e = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    RTDD_TRY(e, "cudaGraphInstantiate");
+    g.exec = exec;
+    g.kernels = kernels;
+    g.resultPlane = result;
+    auto ins = ctx->graphs.emplace(key, g);
+    *out = &ins.first->second;
+    return 0;
+}
+
+int level_dims_ok(const rtdd_ctx *ctx, int level, int rows, int cols)
+{
+    if (level < 0 || level >= ctx->levels) return 0;
+    const RtddLevel &L = ctx->lv[level];
+    return rows >= 1 && cols >= 1 && rows <= L.rows && cols <= L.cols;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rtdd_pyramid_levels(int rows, int cols)
+{
+    // ref: src/main.cpp:95 -- int pyrLevels = log2(std::max(std::min(cols, rows) / 45, 1)) + 1;
+    int m = (cols < rows ? cols : rows) / 45;
+    if (m < 1) m = 1;
+    return (int)log2((double)m) + 1;
+}
+
+int rtdd_level_iterations(int maxIterations, int levels, int level)
+{
+    // ref: src/main.cpp:263 -- int CUDAIteration = maxIterations / powf(2.0, (pyrLevels - 1) - level);
+    return (int)((float)maxIterations / powf(2.0f, (float)((levels - 1) - level)));
+}
+
+int rtdd_create(int rows, int cols, int levels, int device, rtdd_ctx **out)
+{
+    if (!out) return RTDD_E_ARG;
+    *out = nullptr;
+    if (rows < 1 || cols < 1 || levels < 1 || levels > 30) return RTDD_E_ARG;
+    rtdd_ctx *ctx = new (std::nothrow) rtdd_ctx();
+    if (!ctx) return RTDD_E_NOMEM;
+    cudaError_t e;
+    if (device < 0) { e = cudaGetDevice(&device); if (e != cudaSuccess) { delete ctx; return (int)e; } }
+    ctx->device = device;
+    ctx->rows = rows; ctx->cols = cols; ctx->levels = levels;
+    DeviceGuard guard(device);
+    int sm = 0;
+    e = cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, device);
+    if (e != cudaSuccess) { delete ctx; return (int)e; }
+    ctx->smCount = sm > 0 ? sm : 148;
+    e = cudaStreamCreateWithFlags(&ctx->ownStream, cudaStreamDefault);
+    if (e != cudaSuccess) { delete ctx; return (int)e; }
+    ctx->stream = ctx->ownStream;
+    e = cudaStreamCreateWithFlags(&ctx->captureStream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { cudaStreamDestroy(ctx->ownStream); delete ctx; return (int)e; }
+
+    // one arena: per level 4 float planes + 3 byte planes, each with a guard row above and below
+    ctx->lv.resize(levels);
+    size_t total = 257 * sizeof(float) + 256;
+    for (int l = 0; l < levels; l++) {
+        RtddLevel &L = ctx->lv[l];
+        // ref: src/GPUSolver.cu:42-43 -- int rowsPerLevel = rows / powf(2, level)
+        L.rows = (int)((float)rows / powf(2.0f, (float)l));
+        L.cols = (int)((float)cols / powf(2.0f, (float)l));
+        if (L.rows < 1 || L.cols < 1) { L.rows = L.rows < 1 ? 1 : L.rows; L.cols = L.cols < 1 ? 1 : L.cols; }
+        L.pitchF = (int)rtdd_round_up((size_t)L.cols + 4, 64);
+        L.pitchB = (int)rtdd_round_up((size_t)L.cols + 4, 128);
+        total += 4 * rtdd_round_up((size_t)L.pitchF * L.rows * sizeof(float), 256);
+        total += 3 * rtdd_round_up((size_t)L.pitchB * L.rows, 256);
+    }
+    e = cudaMalloc(&ctx->arena, total);
+    if (e != cudaSuccess) { cudaStreamDestroy(ctx->captureStream); cudaStreamDestroy(ctx->ownStream); delete ctx; return (int)e; }
+    ctx->arenaBytes = total;
+    cudaMemsetAsync(ctx->arena, 0, total, ctx->stream);
+    char *p = (char *)ctx->arena;
+    ctx->dLut = (float *)p;
+    p += rtdd_round_up(257 * sizeof(float), 256);
+    for (int l = 0; l < levels; l++) {
+        RtddLevel &L = ctx->lv[l];
+        for (int k = 0; k < 4; k++) { L.x[k] = (float *)p; p += rtdd_round_up((size_t)L.pitchF * L.rows * sizeof(float), 256); }
+        L.linkR = (uint8_t *)p; p += rtdd_round_up((size_t)L.pitchB * L.rows, 256);
+        L.linkD = (uint8_t *)p; p += rtdd_round_up((size_t)L.pitchB * L.rows, 256);
+        L.mask = (uint8_t *)p;  p += rtdd_round_up((size_t)L.pitchB * L.rows, 256);
+    }
+    for (int l = 0; l < levels && e == cudaSuccess; l++) {
+        e = cudaEventCreate(&ctx->lv[l].evBegin);
+        if (e == cudaSuccess) e = cudaEventCreate(&ctx->lv[l].evEnd);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { rtdd_destroy(ctx); return (int)e; }
+    *out = ctx;
+    return 0;
+}
+
+int rtdd_destroy(rtdd_ctx *ctx)
+{
+    if (!ctx) return RTDD_E_ARG;
+    DeviceGuard guard(ctx->device);
+    cudaError_t e = cudaDeviceSynchronize();
+    destroy_graphs(ctx);
+    for (auto &L : ctx->lv) {
+        if (L.evBegin) cudaEventDestroy(L.evBegin);
+        if (L.evEnd) cudaEventDestroy(L.evEnd);
+    }
+    if (ctx->arena) cudaFree(ctx->arena);
+    if (ctx->frameArena) cudaFree(ctx->frameArena);
+    if (ctx->satScratch) cudaFree(ctx->satScratch);
+    if (ctx->captureStream) cudaStreamDestroy(ctx->captureStream);
+    if (ctx->ownStream) cudaStreamDestroy(ctx->ownStream);
+    delete ctx;
+    return (int)e;
+}
+
+int rtdd_load_weights(rtdd_ctx *ctx, float beta)
+{
+    if (!ctx) return RTDD_E_ARG;
+    DeviceGuard guard(ctx->device);
+    // ref: src/GPUSolver.cu:266-268 -- host expf, fp32
+    for (int w = 0; w < 256; w++) ctx->hLut[w] = expf(-beta * w);
+    ctx->hLut[256] = 0.0f;
+    RTDD_TRY(cudaMemcpyAsync(ctx->dLut, ctx->hLut, 257 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream), "rtdd_load_weights");
+    RTDD_TRY(cudaStreamSynchronize(ctx->stream), "rtdd_load_weights");
+    ctx->lutLoaded = true;
+    return 0;
+}
+
+int rtdd_set_stream(rtdd_ctx *ctx, void *stream)
+{
+    if (!ctx) return RTDD_E_ARG;
+    ctx->stream = stream ? (cudaStream_t)stream : ctx->ownStream;
+    return 0;
+}
+
+int rtdd_sync(rtdd_ctx *ctx)
+{
+    if (!ctx) return RTDD_E_ARG;
+    DeviceGuard guard(ctx->device);
+    RTDD_TRY(cudaStreamSynchronize(ctx->stream), "rtdd_sync");
+    RTDD_TRY(cudaGetLastError(), "rtdd_sync");
+    return 0;
+}
+
+const char *rtdd_last_error(const rtdd_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+unsigned long long rtdd_launch_count(const rtdd_ctx *ctx) { return ctx ? ctx->launches : 0ULL; }
+int rtdd_levels(const rtdd_ctx *ctx) { return ctx ? ctx->levels : 0; }
+
+int rtdd_set_sweep_variant(rtdd_ctx *ctx, int variant, int sweepsPerPass)
+{
+    if (!ctx || variant < 0 || variant > 2 || sweepsPerPass < 0 || sweepsPerPass > RTDD_MAX_T) return rtdd_fail(ctx, RTDD_E_ARG, "rtdd_set_sweep_variant");
+    ctx->variant = variant;
+    ctx->sweepsPerPass = sweepsPerPass;
+    return 0;
+}
+
+// ---- the solve ---------------------------------------------------------------
+
+static int edge_pass(rtdd_ctx *ctx, const float *depth, size_t depthPitch, const uint8_t *scribble, size_t scribblePitch,
+                     const uint8_t *gray, size_t grayPitch, int rows, int cols, int level, const char *where)
+{
+    if (!ctx) return RTDD_E_ARG;
+    if (!depth || !gray || !level_dims_ok(ctx, level, rows, cols)) return rtdd_fail(ctx, RTDD_E_ARG, where);
+    RtddLevel &L = ctx->lv[level];
+    if (rows != L.rows || cols != L.cols) return rtdd_fail(ctx, RTDD_E_ARG, where);   // planes are sized per level (ref :42-48)
+    // ref: src/GPUSolver.cu:201-202 -- threshold 4, 0 at level 0; :196 -- ungated on the coarsest level
+    const bool coarsest = (level == ctx->levels - 1);
+    const int threshold = (level == 0) ? 0 : 4;
+    RTDD_TRY(rtdd::launch_level_init(ctx->stream, L, depth, depthPitch, scribble, scribblePitch, gray, grayPitch, coarsest, threshold, L.x[0]), where);
+    ctx->launches++;
+    return 0;
+}
+
+int rtdd_solve_level(rtdd_ctx *ctx, float *depth, size_t depthPitch, const uint8_t *scribble, size_t scribblePitch,
+                     const uint8_t *gray, size_t grayPitch, int rows, int cols, int maxIterations, int level)
+{
+    if (!ctx) return RTDD_E_ARG;
+    if (!ctx->lutLoaded) return rtdd_fail(ctx, RTDD_E_STATE, "rtdd_solve_level (rtdd_load_weights not called)");
+    if (!scribble || maxIterations < 0) return rtdd_fail(ctx, RTDD_E_ARG, "rtdd_solve_level");
+    DeviceGuard guard(ctx->device);
+    int rc = edge_pass(ctx, depth, depthPitch, scribble, scribblePitch, gray, grayPitch, rows, cols, level, "rtdd_solve_level");
+    if (rc) return rc;
+    RtddLevel &L = ctx->lv[level];
+    int plane = 0;
+    if (maxIterations > 0) {
+        RtddGraph *g = nullptr;
+        rc = get_sweep_graph(ctx, level, maxIterations, &g);
+        if (rc) return rc;
+        RTDD_TRY(cudaEventRecord(L.evBegin, ctx->stream), "rtdd_solve_level (event)");
+        RTDD_TRY(cudaGraphLaunch(g->exec, ctx->stream), "rtdd_solve_level (graph launch)");
+        RTDD_TRY(cudaEventRecord(L.evEnd, ctx->stream), "rtdd_solve_level (event)");
+        L.timed = true; L.lastIters = maxIterations; L.lastKernels = g->kernels;
+        ctx->launches += g->kernels;
+        plane = g->resultPlane;
+    }
+    RTDD_TRY(rtdd::launch_copy_out(ctx->stream, L, L.x[plane], depth, depthPitch), "rtdd_solve_level (copy out)");
+    ctx->launches++;
+    return 0;
+}
+
+int rtdd_level_sweep_ms(rtdd_ctx *ctx, int level, float *ms, int *iterations, int *kernels)
+{
+    if (!ctx) return RTDD_E_ARG;
+    if (level < 0 || level >= ctx->levels || !ms) return rtdd_fail(ctx, RTDD_E_ARG, "rtdd_level_sweep_ms");
+    RtddLevel &L = ctx->lv[level];
+    if (!L.timed) return rtdd_fail(ctx, RTDD_E_STATE, "rtdd_level_sweep_ms (level not solved yet)");
+    DeviceGuard guard(ctx->device);
+    RTDD_TRY(cudaEventSynchronize(L.evEnd), "rtdd_level_sweep_ms");
+    RTDD_TRY(cudaEventElapsedTime(ms, L.evBegin, L.evEnd), "rtdd_level_sweep_ms");
+    if (iterations) *iterations = L.lastIters;
+    if (kernels) *kernels = L.lastKernels;
+    return 0;
+}
+
+int rtdd_edge_weights(rtdd_ctx *ctx, const float *depth, size_t depthPitch, const uint8_t *gray, size_t grayPitch,
+                      int rows, int cols, int level, uint8_t *linkRight, uint8_t *linkDown, size_t outPitch)
+{
+    if (!ctx) return RTDD_E_ARG;
+    DeviceGuard guard(ctx->device);
+    // the mask plane is not needed for the links: pass gray as a stand-in scribble plane (any readable u8 plane)
+    int rc = edge_pass(ctx, depth, depthPitch, gray, grayPitch, gray, grayPitch, rows, cols, level, "rtdd_edge_weights");
+    if (rc) return rc;
+    if (linkRight || linkDown) {
+        RTDD_TRY(rtdd::launch_export_links(ctx->stream, ctx->lv[level], linkRight, linkDown, outPitch), "rtdd_edge_weights (export)");
+        ctx->launches++;
+    }
+    return 0;
+}
+
+// ---- GPUImageProcessing --------------------------------------------------------
+
+int rtdd_convert_to_float(rtdd_ctx *ctx, const uint8_t *src, size_t srcPitch, float *dst, size_t dstPitch,
+                          const uint8_t *mask, size_t maskPitch, int rows, int cols)
+{
+    if (!ctx) return RTDD_E_ARG;
+    if (!src || !dst || !mask || rows < 0 || cols < 0) return rtdd_fail(ctx, RTDD_E_ARG, "rtdd_convert_to_float");
+    if (rows == 0 || cols == 0) return 0;
+    DeviceGuard guard(ctx->device);
+    RTDD_TRY(rtdd::launch_convert(ctx->stream, src, srcPitch, dst, dstPitch, mask, maskPitch, rows, cols), "rtdd_convert_to_float");
+    ctx->launches++;
+    return 0;
+}
+
+int rtdd_pyrdown_annotation(rtdd_ctx *ctx, const uint8_t *prevScribble, size_t prevScribblePitch,
+                            const uint8_t *prevEdited, size_t prevEditedPitch, int previousRows, int previousCols,
+                            uint8_t *currScribble, size_t currScribblePitch,
+                            uint8_t *currEdited, size_t currEditedPitch, int currentRows, int currentCols)
+{
+    if (!ctx) return RTDD_E_ARG;
+    if (!prevScribble || !prevEdited || !currScribble || !currEdited || previousRows < 0 || previousCols < 0 || currentRows < 0 || currentCols < 0)
+        return rtdd_fail(ctx, RTDD_E_ARG, "rtdd_pyrdown_annotation");
+    if (currentRows == 0 || currentCols == 0) return 0;
+    DeviceGuard guard(ctx->device);
+    RTDD_TRY(rtdd::launch_pyrdown_annotation(ctx->stream, prevScribble, prevScribblePitch, prevEdited, prevEditedPitch, previousRows, previousCols,
+                                             currScribble, currScribblePitch, currEdited, currEditedPitch, currentRows, currentCols),
+             "rtdd_pyrdown_annotation");
+    ctx->launches++;
+    return 0;
+}
+
+int rtdd_paint(rtdd_ctx *ctx, int x, int y, int scribbleColor, int scribbleRadius,
+               uint8_t *edited, size_t editedPitch, uint8_t *scribble, size_t scribblePitch, int rows, int cols)
+{
+    if (!ctx) return RTDD_E_ARG;
+    if (!edited || !scribble || rows < 0 || cols < 0) return rtdd_fail(ctx, RTDD_E_ARG, "rtdd_paint");
+    DeviceGuard guard(ctx->device);
+    int launched = 0;
+    RTDD_TRY(rtdd::launch_paint(ctx->stream, x, y, scribbleColor, scribbleRadius, edited, editedPitch, scribble, scribblePitch, rows, cols, &launched),
+             "rtdd_paint");
+    ctx->launches += launched;
+    return 0;
+}
+
+// ---- GPUDepthEffect ------------------------------------------------------------
+
+int rtdd_desaturate(rtdd_ctx *ctx, const uint8_t *orig, size_t origPitch, const uint8_t *gray, size_t grayPitch,
+                    const float *depth, size_t depthPitch, uint8_t *out, size_t outPitch, int rows, int cols)
+{
+    if (!ctx) return RTDD_E_ARG;
+    if (!orig || !gray || !depth || !out || rows < 0 || cols < 0) return rtdd_fail(ctx, RTDD_E_ARG, "rtdd_desaturate");
+    if (rows == 0 || cols == 0) return 0;
+    DeviceGuard guard(ctx->device);
+    RTDD_TRY(rtdd::launch_desaturate(ctx->stream, orig, origPitch, gray, grayPitch, depth, depthPitch, out, outPitch, rows, cols), "rtdd_desaturate");
+    ctx->launches++;
+    return 0;
+}
+
+int rtdd_haze(rtdd_ctx *ctx, const uint8_t *orig, size_t origPitch, const float *depth, size_t depthPitch,
+              uint8_t *out, size_t outPitch, int rows, int cols)
+{
+    if (!ctx) return RTDD_E_ARG;
+    if (!orig || !depth || !out || rows < 0 || cols < 0) return rtdd_fail(ctx, RTDD_E_ARG, "rtdd_haze");
+    if (rows == 0 || cols == 0) return 0;
+    DeviceGuard guard(ctx->device);
+    RTDD_TRY(rtdd::launch_haze(ctx->stream, orig, origPitch, depth, depthPitch, out, outPitch, rows, cols), "rtdd_haze");
+    ctx->launches++;
+    return 0;
+}
+
+static int ensure_sat(rtdd_ctx *ctx, int rows, int cols)
+{
+    const size_t need = rtdd::defocus_scratch_bytes(rows, cols);
+    if (need <= ctx->satBytes) return 0;
+    if (ctx->satScratch) { cudaStreamSynchronize(ctx->stream); cudaFree(ctx->satScratch); ctx->satScratch = nullptr; ctx->satBytes = 0; }
+    RTDD_TRY(cudaMalloc(&ctx->satScratch, need), "defocus scratch");
+    ctx->satBytes = need;
+    return 0;
+}
+
+int rtdd_defocus(rtdd_ctx *ctx, const uint8_t *orig, size_t origPitch, const float *depth, size_t depthPitch,
+                 uint8_t *out, size_t outPitch, int rows, int cols)
+{
+    if (!ctx) return RTDD_E_ARG;
+    if (!orig || !depth || !out || rows < 0 || cols < 0) return rtdd_fail(ctx, RTDD_E_ARG, "rtdd_defocus");
+    if (rows == 0 || cols == 0) return 0;
+    DeviceGuard guard(ctx->device);
+    int rc = ensure_sat(ctx, rows, cols);
+    if (rc) return rc;
+    int launched = 0;
+    RTDD_TRY(rtdd::launch_defocus(ctx->stream, ctx->satScratch, orig, origPitch, nullptr, 0, depth, depthPitch, out, outPitch,
+                                  nullptr, 0, nullptr, 0, rows, cols, &launched), "rtdd_defocus");
+    ctx->launches += launched;
+    return 0;
+}
+
+int rtdd_effects_fused(rtdd_ctx *ctx, const uint8_t *orig, size_t origPitch, const uint8_t *gray, size_t grayPitch,
+                       const float *depth, size_t depthPitch, uint8_t *desat, size_t desatPitch, uint8_t *haze, size_t hazePitch,
+                       uint8_t *defocus, size_t defocusPitch, int rows, int cols)
+{
+    if (!ctx) return RTDD_E_ARG;
+    if (!orig || !gray || !depth || !desat || !haze || !defocus || rows < 0 || cols < 0) return rtdd_fail(ctx, RTDD_E_ARG, "rtdd_effects_fused");
+    if (rows == 0 || cols == 0) return 0;
+    DeviceGuard guard(ctx->device);
+    int rc = ensure_sat(ctx, rows, cols);
+    if (rc) return rc;
+    int launched = 0;
+    RTDD_TRY(rtdd::launch_defocus(ctx->stream, ctx->satScratch, orig, origPitch, gray, grayPitch, depth, depthPitch, defocus, defocusPitch,
+                                  desat, desatPitch, haze, hazePitch, rows, cols, &launched), "rtdd_effects_fused");
+    ctx->launches += launched;
+    return 0;
+}
+
+// ---- pyramid ops -----------------------------------------------------------------
+
+int rtdd_bgr2gray(rtdd_ctx *ctx, const uint8_t *bgr, size_t bgrPitch, uint8_t *gray, size_t grayPitch, int rows, int cols)
+{
+    if (!ctx) return RTDD_E_ARG;
+    if (!bgr || !gray || rows < 1 || cols < 1) return rtdd_fail(ctx, RTDD_E_ARG, "rtdd_bgr2gray");
+    DeviceGuard guard(ctx->device);
+    RTDD_TRY(rtdd::launch_bgr2gray(ctx->stream, bgr, bgrPitch, gray, grayPitch, rows, cols), "rtdd_bgr2gray");
+    ctx->launches++;
+    return 0;
+}
+
+int rtdd_pyrdown_gray(rtdd_ctx *ctx, const uint8_t *src, size_t srcPitch, int srcRows, int srcCols, uint8_t *dst, size_t dstPitch)
+{
+    if (!ctx) return RTDD_E_ARG;
+    if (!src || !dst || srcRows < 1 || srcCols < 1) return rtdd_fail(ctx, RTDD_E_ARG, "rtdd_pyrdown_gray");
+    DeviceGuard guard(ctx->device);
+    RTDD_TRY(rtdd::launch_pyrdown_gray(ctx->stream, src, srcPitch, srcRows, srcCols, dst, dstPitch), "rtdd_pyrdown_gray");
+    ctx->launches++;
+    return 0;
+}
+
+int rtdd_pyrup_depth(rtdd_ctx *ctx, const float *src, size_t srcPitch, int srcRows, int srcCols,
+                     float *dst, size_t dstPitch, int dstRows, int dstCols)
+{
+    if (!ctx) return RTDD_E_ARG;
+    if (!src || !dst || srcRows < 1 || srcCols < 1 || dstRows < 2 * srcRows || dstRows > 2 * srcRows + 1 ||
+        dstCols < 2 * srcCols || dstCols > 2 * srcCols + 1)
+        return rtdd_fail(ctx, RTDD_E_ARG, "rtdd_pyrup_depth");
+    DeviceGuard guard(ctx->device);
+    RTDD_TRY(rtdd::launch_pyrup_depth(ctx->stream, src, srcPitch, srcRows, srcCols, dst, dstPitch, dstRows, dstCols), "rtdd_pyrup_depth");
+    ctx->launches++;
+    return 0;
+}
+
+int rtdd_quantise_u8(rtdd_ctx *ctx, const float *src, size_t srcPitch, uint8_t *dst, size_t dstPitch, int rows, int cols)
+{
+    if (!ctx) return RTDD_E_ARG;
+    if (!src || !dst || rows < 1 || cols < 1) return rtdd_fail(ctx, RTDD_E_ARG, "rtdd_quantise_u8");
+    DeviceGuard guard(ctx->device);
+    RTDD_TRY(rtdd::launch_quantise(ctx->stream, src, srcPitch, dst, dstPitch, rows, cols), "rtdd_quantise_u8");
+    ctx->launches++;
+    return 0;
+}
+
+// ---- frame driver (main.cpp:232-295 restated headless) -----------------------------
+
+static int frame_alloc(rtdd_ctx *ctx)
+{
+    if (ctx->frameArena) return 0;
+    ctx->fl.resize(ctx->levels);
+    size_t total = 0;
+    int gr = ctx->rows, gc = ctx->cols;   // gray sizes follow cv::pyrDown's ceil rule from the (ceil) level above
+    for (int l = 0; l < ctx->levels; l++) {
+        RtddFrameLevel &F = ctx->fl[l];
+        F.rows = ctx->lv[l].rows; F.cols = ctx->lv[l].cols;
+        if (l > 0) { gr = (gr + 1) / 2; gc = (gc + 1) / 2; }
+        F.grayRows = gr; F.grayCols = gc;
+        F.depthPitch = rtdd_round_up((size_t)F.cols * sizeof(float), 512);
+        F.grayPitch = rtdd_round_up((size_t)F.grayCols, 512);
+        F.scribblePitch = rtdd_round_up((size_t)F.cols, 512);
+        F.editedPitch = rtdd_round_up((size_t)F.cols * 3, 512);
+        total += F.depthPitch * F.rows + F.grayPitch * F.grayRows + F.scribblePitch * F.rows + F.editedPitch * F.rows;
+    }
+    ctx->bgrPitch = rtdd_round_up((size_t)ctx->cols * 3, 512);
+    ctx->depthU8Pitch = rtdd_round_up((size_t)ctx->cols, 512);
+    total += ctx->bgrPitch * ctx->rows + ctx->depthU8Pitch * ctx->rows;
+    RTDD_TRY(cudaMalloc(&ctx->frameArena, total), "frame arena");
+    char *p = (char *)ctx->frameArena;
+    for (int l = 0; l < ctx->levels; l++) {
+        RtddFrameLevel &F = ctx->fl[l];
+        F.depth = (float *)p; p += F.depthPitch * F.rows;
+        F.gray = (uint8_t *)p; p += F.grayPitch * F.grayRows;
+        F.scribble = (uint8_t *)p; p += F.scribblePitch * F.rows;
+        F.edited = (uint8_t *)p; p += F.editedPitch * F.rows;
+    }
+    ctx->bgr = (uint8_t *)p; p += ctx->bgrPitch * ctx->rows;
+    ctx->depthU8 = (uint8_t *)p;
+    return 0;
+}
+
+int rtdd_frame_set_image(rtdd_ctx *ctx, const uint8_t *bgrHost, size_t bgrPitch)
+{
+    if (!ctx) return RTDD_E_ARG;
+    if (!bgrHost || bgrPitch < (size_t)ctx->cols * 3) return rtdd_fail(ctx, RTDD_E_ARG, "rtdd_frame_set_image");
+    DeviceGuard guard(ctx->device);
+    int rc = frame_alloc(ctx);
+    if (rc) return rc;
+    cudaStream_t s = ctx->stream;
+    RTDD_TRY(cudaMemcpy2DAsync(ctx->bgr, ctx->bgrPitch, bgrHost, bgrPitch, (size_t)ctx->cols * 3, ctx->rows, cudaMemcpyHostToDevice, s),
+             "rtdd_frame_set_image (upload)");
+    // annotation planes start at 0, depth planes at 255 (ref: src/main.cpp:130-136)
+    for (int l = 0; l < ctx->levels; l++) {
+        RtddFrameLevel &F = ctx->fl[l];
+        RTDD_TRY(cudaMemsetAsync(F.scribble, 0, F.scribblePitch * F.rows, s), "rtdd_frame_set_image");
+        RTDD_TRY(cudaMemsetAsync(F.edited, 0, F.editedPitch * F.rows, s), "rtdd_frame_set_image");
+        RTDD_TRY(rtdd::launch_fill_f32(s, F.depth, F.depthPitch, F.rows, F.cols, 255.0f), "rtdd_frame_set_image");
+        ctx->launches++;
+    }
+    // gray pyramid (ref: src/main.cpp:138-147); cached across frames because the image does not change
+    RTDD_TRY(rtdd::launch_bgr2gray(s, ctx->bgr, ctx->bgrPitch, ctx->fl[0].gray, ctx->fl[0].grayPitch, ctx->rows, ctx->cols), "rtdd_frame_set_image");
+    ctx->launches++;
+    for (int l = 1; l < ctx->levels; l++) {
+        RtddFrameLevel &P = ctx->fl[l - 1], &F = ctx->fl[l];
+        RTDD_TRY(rtdd::launch_pyrdown_gray(s, P.gray, P.grayPitch, P.grayRows, P.grayCols, F.gray, F.grayPitch), "rtdd_frame_set_image");
+        ctx->launches++;
+    }
+    ctx->imageSet = true;
+    return 0;
+}
+
+int rtdd_frame_solve(rtdd_ctx *ctx, int maxIterations)
+{
+    if (!ctx) return RTDD_E_ARG;
+    if (!ctx->imageSet || !ctx->lutLoaded) return rtdd_fail(ctx, RTDD_E_STATE, "rtdd_frame_solve");
+    DeviceGuard guard(ctx->device);
+    const int Lc = ctx->levels - 1;
+    int rc;
+    for (int l = 1; l < ctx->levels; l++) {                               // main.cpp:249
+        RtddFrameLevel &P = ctx->fl[l - 1], &F = ctx->fl[l];
+        rc = rtdd_pyrdown_annotation(ctx, P.scribble, P.scribblePitch, P.edited, P.editedPitch, P.rows, P.cols,
+                                     F.scribble, F.scribblePitch, F.edited, F.editedPitch, F.rows, F.cols);
+        if (rc) return rc;
+    }
+    {
+        RtddFrameLevel &F = ctx->fl[Lc];                                      // main.cpp:257
+        rc = rtdd_convert_to_float(ctx, F.edited, F.editedPitch, F.depth, F.depthPitch, F.scribble, F.scribblePitch, F.rows, F.cols);
+        if (rc) return rc;
+    }
+    for (int l = Lc; l >= 0; l--) {                                           // main.cpp:261-288
+        RtddFrameLevel &F = ctx->fl[l];
+        const int iters = rtdd_level_iterations(maxIterations, ctx->levels, l);
+        rc = rtdd_solve_level(ctx, F.depth, F.depthPitch, F.scribble, F.scribblePitch, F.gray, F.grayPitch, F.rows, F.cols, iters, l);
+        if (rc) return rc;
+        if (l > 0) {
+            RtddFrameLevel &N = ctx->fl[l - 1];
+            rc = rtdd_pyrup_depth(ctx, F.depth, F.depthPitch, F.rows, F.cols, N.depth, N.depthPitch, N.rows, N.cols);
+            if (rc) return rc;
+            rc = rtdd_convert_to_float(ctx, N.edited, N.editedPitch, N.depth, N.depthPitch, N.scribble, N.scribblePitch, N.rows, N.cols);
+            if (rc) return rc;
+        }
+    }
+    return rtdd_quantise_u8(ctx, ctx->fl[0].depth, ctx->fl[0].depthPitch, ctx->depthU8, ctx->depthU8Pitch, ctx->rows, ctx->cols);  // main.cpp:290
+}
+
+int rtdd_frame_solve_host(rtdd_ctx *ctx, const uint8_t *scribbleHost, size_t scribblePitch,
+                          const uint8_t *editedHost, size_t editedPitch, int maxIterations, uint8_t *depthU8Host, size_t depthU8Pitch)
+{
+    if (!ctx) return RTDD_E_ARG;
+    if (!ctx->imageSet) return rtdd_fail(ctx, RTDD_E_STATE, "rtdd_frame_solve_host");
+    if (!scribbleHost || !editedHost || scribblePitch < (size_t)ctx->cols || editedPitch < (size_t)ctx->cols * 3 ||
+        (depthU8Host && depthU8Pitch < (size_t)ctx->cols))
+        return rtdd_fail(ctx, RTDD_E_ARG, "rtdd_frame_solve_host");
+    DeviceGuard guard(ctx->device);
+    cudaStream_t s = ctx->stream;
+    RtddFrameLevel &F = ctx->fl[0];
+    RTDD_TRY(cudaMemcpy2DAsync(F.scribble, F.scribblePitch, scribbleHost, scribblePitch, (size_t)ctx->cols, ctx->rows, cudaMemcpyHostToDevice, s),
+             "rtdd_frame_solve_host (scribble upload)");                       // main.cpp:236
+    RTDD_TRY(cudaMemcpy2DAsync(F.edited, F.editedPitch, editedHost, editedPitch, (size_t)ctx->cols * 3, ctx->rows, cudaMemcpyHostToDevice, s),
+             "rtdd_frame_solve_host (edited upload)");                         // main.cpp:237
+    int rc = rtdd_frame_solve(ctx, maxIterations);
+    if (rc) return rc;
+    if (depthU8Host) {
+        RTDD_TRY(cudaMemcpy2DAsync(depthU8Host, depthU8Pitch, ctx->depthU8, ctx->depthU8Pitch, (size_t)ctx->cols, ctx->rows, cudaMemcpyDeviceToHost, s),
+                 "rtdd_frame_solve_host (download)");                          // main.cpp:291
+        RTDD_TRY(cudaStreamSynchronize(s), "rtdd_frame_solve_host");
+    }
+    return 0;
+}
+
+int rtdd_frame_paint(rtdd_ctx *ctx, int x, int y, int scribbleColor, int scribbleRadius)
+{
+    if (!ctx) return RTDD_E_ARG;
+    if (!ctx->imageSet) return rtdd_fail(ctx, RTDD_E_STATE, "rtdd_frame_paint");
+    RtddFrameLevel &F = ctx->fl[0];
+    return rtdd_paint(ctx, x, y, scribbleColor, scribbleRadius, F.edited, F.editedPitch, F.scribble, F.scribblePitch, F.rows, F.cols);
+}
+
+int rtdd_frame_plane(rtdd_ctx *ctx, int which, int level, void **ptr, size_t *pitch, int *rows, int *cols)
+{
+    if (!ctx) return RTDD_E_ARG;
+    if (!ctx->frameArena) { DeviceGuard guard(ctx->device); int rc = frame_alloc(ctx); if (rc) return rc; }
+    if (level < 0 || level >= ctx->levels) return rtdd_fail(ctx, RTDD_E_ARG, "rtdd_frame_plane");
+    RtddFrameLevel &F = ctx->fl[level];
+    void *p = nullptr; size_t pi = 0; int r = F.rows, c = F.cols;
+    switch (which) {
+    case RTDD_PLANE_DEPTH: p = F.depth; pi = F.depthPitch; break;
+    case RTDD_PLANE_GRAY: p = F.gray; pi = F.grayPitch; r = F.grayRows; c = F.grayCols; break;
+    case RTDD_PLANE_SCRIBBLE: p = F.scribble; pi = F.scribblePitch; break;
+    case RTDD_PLANE_EDITED: p = F.edited; pi = F.editedPitch; break;
+    case RTDD_PLANE_BGR: if (level != 0) return rtdd_fail(ctx, RTDD_E_ARG, "rtdd_frame_plane"); p = ctx->bgr; pi = ctx->bgrPitch; break;
+    case RTDD_PLANE_DEPTH_U8: if (level != 0) return rtdd_fail(ctx, RTDD_E_ARG, "rtdd_frame_plane"); p = ctx->depthU8; pi = ctx->depthU8Pitch; break;
+    default: return rtdd_fail(ctx, RTDD_E_ARG, "rtdd_frame_plane");
+    }
+    if (ptr) *ptr = p;
+    if (pitch) *pitch = pi;
+    if (rows) *rows = r;
+    if (cols) *cols = c;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,138 @@
+// Internal declarations shared by the translation units of librtdd.so.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "rtdd.h"
+
+// One pyramid level's scratch in the HBM arena.  Float planes share one row pitch
+// (pitchF floats, a multiple of 64 => rows start 256 B aligned, TMA-legal); byte
+// planes share pitchB (a multiple of 128).  Padding columns/rows are zero.
+struct RtddLevel {
+    int rows = 0, cols = 0;
+    int pitchF = 0;            // floats per row of x[] planes
+    int pitchB = 0;            // bytes per row of link/mask planes
+    float *x[4] = {nullptr, nullptr, nullptr, nullptr};   // rotating iterate planes
+    uint8_t *linkR = nullptr;  // LUT index of link (x,y)-(x+1,y)
+    uint8_t *linkD = nullptr;  // LUT index of link (x,y)-(x,y+1)
+    uint8_t *mask = nullptr;   // 0xFF where the scribble plane == 255 (Dirichlet), else 0
+    // events bracketing the most recent sweep graph of this level (rtdd_level_sweep_ms)
+    cudaEvent_t evBegin = nullptr, evEnd = nullptr;
+    bool timed = false;
+    int lastIters = 0, lastKernels = 0;
+};
+
+// Context-owned images of the frame driver (what main.cpp keeps in GpuMat vectors).
+struct RtddFrameLevel {
+    int rows = 0, cols = 0;        // floor sizes (depth / scribble / edited)
+    int grayRows = 0, grayCols = 0; // ceil sizes (cv::pyrDown output)
+    float *depth = nullptr;   size_t depthPitch = 0;
+    uint8_t *gray = nullptr;  size_t grayPitch = 0;
+    uint8_t *scribble = nullptr; size_t scribblePitch = 0;
+    uint8_t *edited = nullptr;   size_t editedPitch = 0;
+};
+
+struct RtddGraphKey {
+    int level, iters, variant, T;
+    bool operator<(const RtddGraphKey &o) const {
+        if (level != o.level) return level < o.level;
+        if (iters != o.iters) return iters < o.iters;
+        if (variant != o.variant) return variant < o.variant;
+        return T < o.T;
+    }
+};
+
+struct RtddGraph {
+    cudaGraphExec_t exec = nullptr;
+    int kernels = 0;
+    int resultPlane = 0;   // index into RtddLevel::x holding x_K after the graph ran
+};
+
+struct rtdd_ctx {
+    int device = 0;
+    int rows = 0, cols = 0, levels = 0;
+    int smCount = 148;
+    cudaStream_t ownStream = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaStream_t captureStream = nullptr;   // private non-blocking stream used only to capture sweep graphs
+    void *arena = nullptr;
+    size_t arenaBytes = 0;
+    std::vector<RtddLevel> lv;
+    float *dLut = nullptr;       // 257 floats
+    float hLut[257];
+    bool lutLoaded = false;
+    int variant = 0;             // 0 auto, 1 single-sweep, 2 temporally blocked
+    int sweepsPerPass = 0;       // 0 auto
+    std::map<RtddGraphKey, RtddGraph> graphs;
+    unsigned long long launches = 0;
+    std::string err;
+    // frame driver state
+    std::vector<RtddFrameLevel> fl;
+    void *frameArena = nullptr;
+    uint8_t *bgr = nullptr; size_t bgrPitch = 0;
+    uint8_t *depthU8 = nullptr; size_t depthU8Pitch = 0;
+    bool imageSet = false;
+    // defocus scratch (summed-area tables), grown on demand
+    void *satScratch = nullptr; size_t satBytes = 0;
+};
+
+int rtdd_fail(rtdd_ctx *ctx, int code, const char *where);
+int rtdd_check(rtdd_ctx *ctx, cudaError_t e, const char *where);
+
+static inline int rtdd_div_up(int a, int b) { return (a + b - 1) / b; }
+static inline size_t rtdd_round_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
+
+// ---- kernel launchers (defined in the .cu translation units) ----------------
+namespace rtdd {
+
+// solver_kernels.cu
+cudaError_t launch_level_init(cudaStream_t s, const RtddLevel &L, const float *depth, size_t depthPitch,
+                              const uint8_t *scribble, size_t scribblePitch,
+                              const uint8_t *gray, size_t grayPitch, bool coarsest, int threshold, float *x0);
+cudaError_t launch_sweep_single(cudaStream_t s, const RtddLevel &L, const float *lut, const float *x, const float *prev,
+                                float *out, float omega, float gamma, bool firstSweep);
+// temporally blocked: T sweeps (x, prev) -> (xOut, prevOut); omegas passed by value (<= RTDD_MAX_T)
+#define RTDD_MAX_T 16
+struct OmegaPack { float w[RTDD_MAX_T]; };
+cudaError_t launch_sweep_blocked(cudaStream_t s, const RtddLevel &L, const float *lut, const float *x, const float *prev,
+                                 float *xOut, float *prevOut, OmegaPack om, int T, int nsweeps, float gamma, bool firstSweep, int smCount);
+int blocked_max_T();
+cudaError_t launch_copy_out(cudaStream_t s, const RtddLevel &L, const float *x, float *depth, size_t depthPitch);
+cudaError_t launch_export_links(cudaStream_t s, const RtddLevel &L, uint8_t *linkRight, uint8_t *linkDown, size_t outPitch);
+
+// image_kernels.cu
+cudaError_t launch_convert(cudaStream_t s, const uint8_t *src, size_t srcPitch, float *dst, size_t dstPitch,
+                           const uint8_t *mask, size_t maskPitch, int rows, int cols);
+cudaError_t launch_pyrdown_annotation(cudaStream_t s, const uint8_t *prevScribble, size_t prevScribblePitch,
+                                      const uint8_t *prevEdited, size_t prevEditedPitch, int previousRows, int previousCols,
+                                      uint8_t *currScribble, size_t currScribblePitch, uint8_t *currEdited, size_t currEditedPitch,
+                                      int currentRows, int currentCols);
+cudaError_t launch_paint(cudaStream_t s, int x, int y, int color, int radius, uint8_t *edited, size_t editedPitch,
+                         uint8_t *scribble, size_t scribblePitch, int rows, int cols, int *launched);
+cudaError_t launch_bgr2gray(cudaStream_t s, const uint8_t *bgr, size_t bgrPitch, uint8_t *gray, size_t grayPitch, int rows, int cols);
+cudaError_t launch_pyrdown_gray(cudaStream_t s, const uint8_t *src, size_t srcPitch, int srows, int scols, uint8_t *dst, size_t dstPitch);
+cudaError_t launch_pyrup_depth(cudaStream_t s, const float *src, size_t srcPitch, int srows, int scols,
+                               float *dst, size_t dstPitch, int drows, int dcols);
+cudaError_t launch_quantise(cudaStream_t s, const float *src, size_t srcPitch, uint8_t *dst, size_t dstPitch, int rows, int cols);
+cudaError_t launch_fill_f32(cudaStream_t s, float *dst, size_t pitch, int rows, int cols, float v);
+
+// effect_kernels.cu
+cudaError_t launch_desaturate(cudaStream_t s, const uint8_t *orig, size_t origPitch, const uint8_t *gray, size_t grayPitch,
+                              const float *depth, size_t depthPitch, uint8_t *out, size_t outPitch, int rows, int cols);
+cudaError_t launch_haze(cudaStream_t s, const uint8_t *orig, size_t origPitch, const float *depth, size_t depthPitch,
+                        uint8_t *out, size_t outPitch, int rows, int cols);
+int defocus_kernel_size(int rows, int cols);
+size_t defocus_scratch_bytes(int rows, int cols);
+// desat/haze may be null (defocus only); returns number of kernels launched through *launched
+cudaError_t launch_defocus(cudaStream_t s, void *scratch, const uint8_t *orig, size_t origPitch, const uint8_t *gray, size_t grayPitch,
+                           const float *depth, size_t depthPitch, uint8_t *defocus, size_t defocusPitch,
+                           uint8_t *desat, size_t desatPitch, uint8_t *haze, size_t hazePitch,
+                           int rows, int cols, int *launched);
+
+}  // namespace rtdd

@@ -1,0 +1,376 @@
+"""GPU parity tests (run on the B200 box): librtdd.so through its C ABI and through the
+reference-named C++ shims, against (1) the CPU oracle, (2) the reference's own kernels
+(oracle/_ref/libref.so) in the same process, (3) the committed golden vectors.
+
+Bars: solver floats BIT-EXACT (stronger than north_star's 1e-4 relative L-inf, which the chained
+pyramid needs anyway -- SURVEY.md fact 6); u8 outputs identical, except haze against the CPU
+oracle (glibc expf vs libdevice expf: <= 1 grey level on < 0.1 % of values) -- haze against the
+reference's own kernel is identical."""
+import ctypes as C
+import hashlib
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import binding as ob
+from realtimedepthdiffusion_b200 import synth
+from tests.harness import MainLoop, pitch, ptr, to_dev, to_host
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+@pytest.fixture(scope="module")
+def rtdd():
+    import realtimedepthdiffusion_b200 as pkg
+    return pkg
+
+
+def random_level(rows, cols, seed, scribble_frac=0.1):
+    rng = np.random.default_rng(seed)
+    gray = synth.synth_image(rows, cols, seed)[..., 1].copy()
+    depth = (rng.integers(0, 5, (rows, cols)) * 60 + rng.uniform(0, 14, (rows, cols))).astype(np.float32)
+    scribble = np.where(rng.random((rows, cols)) < scribble_frac, 255, rng.integers(0, 255, (rows, cols))).astype(np.uint8)
+    return gray, depth, scribble
+
+
+SIZES = [(1, 1), (1, 7), (9, 1), (2, 2), (16, 16), (17, 33), (67, 120), (135, 240), (64, 128), (65, 129),
+         (100, 257), (203, 317), (270, 480)]
+
+
+@pytest.mark.parametrize("rows,cols", SIZES)
+@pytest.mark.parametrize("variant,T", [(1, 0), (2, 1), (2, 4), (2, 7), (2, 8), (2, 12), (2, 16), (0, 0)])
+def test_solve_level_bit_exact_vs_oracle(rtdd, rows, cols, variant, T):
+    iters = 37
+    for level, levels in ((0, 2), (1, 3), (2, 3)):
+        gray, depth, scribble = random_level(rows, cols, 100 + rows + cols + level)
+        want = ob.solve_level(depth, scribble, gray, iters, level, levels - 1)
+        ctx = rtdd.DepthDiffusion(rows << level, cols << level, levels)
+        ctx.set_sweep_variant(variant, T)
+        d, s, g = to_dev(depth), to_dev(scribble), to_dev(gray)
+        ctx.matrix_free_solver(d, s, g, iters, level)
+        ctx.sync()
+        got = to_host(d)
+        ctx.close()
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), \
+            "level %d: max |diff| %g on %d px" % (level, np.abs(got - want).max(), (got != want).sum())
+
+
+@pytest.mark.parametrize("iters", [0, 1, 2, 9, 10, 11, 12, 64])
+def test_iteration_counts_and_result_plane(rtdd, iters):
+    rows, cols = 70, 150
+    gray, depth, scribble = random_level(rows, cols, 5)
+    want = ob.solve_level(depth, scribble, gray, iters, 0, 0)
+    for variant, T in ((1, 0), (2, 8), (2, 5)):
+        ctx = rtdd.DepthDiffusion(rows, cols, 1)
+        ctx.set_sweep_variant(variant, T)
+        d, s, g = to_dev(depth), to_dev(scribble), to_dev(gray)
+        ctx.matrix_free_solver(d, s, g, iters, 0)
+        ctx.sync()
+        assert np.array_equal(to_host(d).view(np.uint32), want.view(np.uint32)), (variant, T)
+        ctx.close()
+
+
+def test_edge_cases_all_scribble_no_scribble_extreme_depths(rtdd):
+    rows, cols = 40, 90
+    gray, depth, scribble = random_level(rows, cols, 6)
+    depth[3, 4] = 300.7
+    depth[5, 6] = -4.0
+    depth[7, 8] = 256.0
+    for scr in (np.full((rows, cols), 255, np.uint8), np.zeros((rows, cols), np.uint8), scribble):
+        want = ob.solve_level(depth, scr, gray, 25, 1, 2)
+        ctx = rtdd.DepthDiffusion(rows * 2, cols * 2, 3)
+        d, s, g = to_dev(depth), to_dev(scr), to_dev(gray)
+        ctx.matrix_free_solver(d, s, g, 25, 1)
+        ctx.sync()
+        assert np.array_equal(to_host(d).view(np.uint32), want.view(np.uint32))
+        ctx.close()
+
+
+def test_gray_plane_larger_than_depth_plane(rtdd):
+    """cv::pyrDown gives ceil-sized gray levels; only the pitch matters."""
+    rows, cols = 67, 120
+    gray, depth, scribble = random_level(rows + 1, cols + 1, 8)
+    depth, scribble = depth[:rows, :cols].copy(), scribble[:rows, :cols].copy()
+    want = ob.solve_level(depth, scribble, gray, 30, 0, 0)
+    ctx = rtdd.DepthDiffusion(rows, cols, 1)
+    d, s, g = to_dev(depth), to_dev(scribble), to_dev(gray)
+    ctx.matrix_free_solver(d, s, g[:rows, :cols], 30, 0)
+    ctx.sync()
+    assert np.array_equal(to_host(d).view(np.uint32), want.view(np.uint32))
+    ctx.close()
+
+
+@pytest.mark.parametrize("rows,cols,level,levels", [(67, 120, 2, 3), (135, 240, 1, 3), (97, 131, 0, 2), (1, 5, 0, 1), (6, 1, 1, 2)])
+def test_edge_weight_pass_vs_oracle(rtdd, rows, cols, level, levels):
+    gray, depth, _ = random_level(rows, cols, 9 + rows)
+    depth[0, 0] = 300.7
+    depth[-1, -1] = -3.5
+    idx = ob.index_to_weight(gray, depth, level, levels - 1)
+    wr, wd = ob.links_from_index(idx)
+    # the oracle's 4-index plane is symmetric: left(x) == right(x-1), up(y) == down(y-1)
+    if cols > 1:
+        assert (idx[:, 1:, 0] == idx[:, :-1, 1]).all()
+    if rows > 1:
+        assert (idx[1:, :, 2] == idx[:-1, :, 3]).all()
+    ctx = rtdd.DepthDiffusion(rows << level, cols << level, levels)
+    r, d = ctx.edge_weights(to_dev(depth), to_dev(gray), level)
+    ctx.sync()
+    assert (to_host(r) == wr).all() and (to_host(d) == wd).all()
+    ctx.close()
+
+
+def test_call_order_and_argument_errors(rtdd):
+    ctx = rtdd.DepthDiffusion(64, 64, 1, beta=None)
+    d, s, g = to_dev(np.zeros((64, 64), np.float32)), to_dev(np.zeros((64, 64), np.uint8)), to_dev(np.zeros((64, 64), np.uint8))
+    with pytest.raises(rtdd.RtddError):
+        ctx.matrix_free_solver(d, s, g, 3, 0)        # GPULoadWeights not called yet
+    ctx.load_weights(0.4)
+    with pytest.raises(rtdd.RtddError):
+        ctx.matrix_free_solver(d, s, g, 3, 1)        # level out of range
+    with pytest.raises(rtdd.RtddError):
+        ctx.matrix_free_solver(d[:32], s[:32], g[:32], 3, 0)   # size does not match the level's planes
+    ctx.matrix_free_solver(d, s, g, 3, 0)
+    ctx.sync()
+    assert ctx.launch_count >= 3
+    ctx.close()
+
+
+# ---- image processing + pyramid ops -------------------------------------------------------
+
+@pytest.mark.parametrize("rows,cols", [(1, 1), (11, 14), (67, 120), (203, 317)])
+def test_image_processing_vs_oracle(rtdd, rows, cols):
+    rng = np.random.default_rng(rows * cols)
+    ctx = rtdd.DepthDiffusion(max(rows, 2), max(cols, 2), 1)
+    src = rng.integers(0, 256, (rows, cols, 3), dtype=np.uint8)
+    mask = np.where(rng.random((rows, cols)) < 0.3, 255, rng.integers(0, 255, (rows, cols))).astype(np.uint8)
+    dst = rng.uniform(0, 255, (rows, cols)).astype(np.float32)
+    dd = to_dev(dst)
+    ctx.convert_to_float(to_dev(src, 3), dd, to_dev(mask))
+    assert np.array_equal(to_host(dd), ob.convert_to_float(src, dst, mask))
+    cr, cc = rows // 2, cols // 2
+    if cr and cc:
+        cs0 = rng.integers(0, 2, (cr, cc), dtype=np.uint8) * 7
+        ce0 = rng.integers(0, 256, (cr, cc, 3), dtype=np.uint8)
+        dcs, dce = to_dev(cs0), to_dev(ce0, 3)
+        ctx.pyrdown_annotation(to_dev(mask), to_dev(src, 3), dcs, dce)
+        ws, we = ob.pyrdown_annotation(mask, src, cs0, ce0)
+        assert np.array_equal(to_host(dcs), ws) and np.array_equal(to_host(dce, 3), we)
+    for (x, y, col, rad) in ((0, 0, 64, 5), (cols - 1, rows - 1, 254, 8), (cols // 2, rows // 2, 128, 21), (-3, 4, 1, 4), (cols + 30, 2, 1, 4),
+                             (3, 3, 9, 0), (3, 3, 9, 1), (2, 2, 300, 3)):
+        e0 = rng.integers(0, 256, (rows, cols, 3), dtype=np.uint8)
+        s0 = np.zeros((rows, cols), np.uint8)
+        de, ds = to_dev(e0, 3), to_dev(s0)
+        ctx.paint_image(x, y, col, rad, de, ds)
+        we, ws = ob.paint(x, y, col, rad, e0, s0)
+        assert np.array_equal(to_host(de, 3), we) and np.array_equal(to_host(ds), ws), (x, y, col, rad)
+    ctx.close()
+
+
+@pytest.mark.parametrize("rows,cols", [(2, 2), (67, 120), (135, 241), (50, 51), (3, 9)])
+def test_pyramid_ops_vs_oracle(rtdd, rows, cols):
+    rng = np.random.default_rng(rows + cols)
+    ctx = rtdd.DepthDiffusion(rows, cols, 1)
+    bgr = rng.integers(0, 256, (rows, cols, 3), dtype=np.uint8)
+    g = to_dev(np.zeros((rows, cols), np.uint8))
+    ctx.bgr2gray(to_dev(bgr, 3), g)
+    gray = ob.bgr2gray(bgr)
+    assert np.array_equal(to_host(g), gray)
+    dn = to_dev(np.zeros(((rows + 1) // 2, (cols + 1) // 2), np.uint8))
+    ctx.pyrdown_gray(g, dn)
+    assert np.array_equal(to_host(dn), ob.pyrdown_gray(gray))
+    f = rng.uniform(-5, 260, (rows, cols)).astype(np.float32)
+    f[0, 0] = 0.5
+    f[-1, -1] = 1.5
+    f[0, -1] = 2.5
+    q = to_dev(np.zeros((rows, cols), np.uint8))
+    ctx.quantise_u8(to_dev(f), q)
+    assert np.array_equal(to_host(q), ob.quantise_u8(f))
+    for dr, dc in ((2 * rows, 2 * cols), (2 * rows + 1, 2 * cols + 1), (2 * rows, 2 * cols + 1), (2 * rows + 1, 2 * cols)):
+        up = to_dev(np.zeros((dr, dc), np.float32))
+        ctx.pyrup_depth(to_dev(f), up)
+        want = ob.pyrup_f32(f, dr, dc)
+        assert np.array_equal(to_host(up).view(np.uint32), want.view(np.uint32)), (dr, dc)
+    ctx.close()
+
+
+# ---- effects --------------------------------------------------------------------------------
+
+def effect_inputs(rows, cols, seed):
+    rng = np.random.default_rng(seed)
+    bgr = synth.synth_image(rows, cols, seed)
+    gray = ob.bgr2gray(bgr)
+    yy, xx = np.mgrid[0:rows, 0:cols]
+    depth = (255.0 * (0.5 + 0.5 * np.sin(xx / 37.0) * np.cos(yy / 23.0))).astype(np.float32)
+    depth += rng.uniform(-0.5, 0.5, depth.shape).astype(np.float32)
+    depth[0, :5] = [0.0, -7.0, 255.0, 262.5, 1.0]
+    return bgr, gray, depth
+
+
+@pytest.mark.parametrize("rows,cols", [(1, 1), (5, 3), (67, 121), (203, 317), (270, 480)])
+def test_effects_vs_oracle(rtdd, rows, cols):
+    bgr, gray, depth = effect_inputs(rows, cols, 21)
+    if rows == 1:
+        depth[:] = 200.0
+    ctx = rtdd.DepthDiffusion(max(rows, 2), max(cols, 2), 1)
+    o, g, d = to_dev(bgr, 3), to_dev(gray), to_dev(depth)
+    outs = [to_dev(np.zeros_like(bgr), 3) for _ in range(6)]
+    ctx.simulate_desaturation(o, g, d, outs[0])
+    ctx.simulate_haze(o, d, outs[1])
+    ctx.simulate_defocus(o, d, outs[2])
+    ctx.effects_fused(o, g, d, outs[3], outs[4], outs[5])
+    ctx.sync()
+    got = [to_host(t, 3) for t in outs]
+    assert np.array_equal(got[0], ob.desaturate(bgr, gray, depth))
+    assert np.array_equal(got[2], ob.defocus(bgr, depth))
+    h = got[1].astype(np.int16) - ob.haze(bgr, depth).astype(np.int16)
+    assert np.abs(h).max() <= 1 and (h != 0).mean() < 1e-3
+    for a, b in zip(got[:3], got[3:]):
+        assert np.array_equal(a, b)                 # fused == separate, bit for bit
+    # unaligned planes (odd pitch) take the byte path and give the same result
+    ou = torch.empty((rows, cols * 3 + 1), dtype=torch.uint8, device="cuda")[:, : cols * 3]
+    ou.copy_(o)
+    out_u = torch.zeros((rows, cols * 3 + 5), dtype=torch.uint8, device="cuda")[:, : cols * 3]
+    ctx.simulate_desaturation(ou, g, d, out_u)
+    ctx.sync()
+    assert np.array_equal(to_host(out_u, 3), got[0])
+    ctx.close()
+
+
+# ---- A/B against the reference's own kernels in the same process --------------------------------
+
+def have_ref():
+    return os.path.exists(ob.LIBREF)
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref/libref.so not built")
+@pytest.mark.parametrize("name", ["synth_tiny", "synth_odd", "dog"])
+def test_main_loop_ab_reference_vs_shims(name):
+    """The same restated main.cpp loop, once over the reference's functions and once over ours."""
+    from realtimedepthdiffusion_b200 import _native
+    from tests.test_oracle_cpu import _load_case
+    bgr, scribble, edited = _load_case(name)
+    iters = {"dog": 1000, "synth_odd": 200, "synth_tiny": 60}[name]
+    res = {}
+    for tag, api in (("ref", ob.ref_api()), ("new", _native.shims)):
+        loop = MainLoop(api, bgr)
+        u8 = loop.frame(scribble, edited, iters, keep_levels=True)
+        ev = synth.brush_events(loop.rows, loop.cols, 99, 1, 6)
+        s2, e2 = synth.paint_events(bgr, ev, scribble.copy(), edited.copy())
+        u8b = loop.frame(s2, e2, iters)
+        res[tag] = (u8, {l: d["out"] for l, d in loop.per_level.items()}, u8b, loop.depth_float)
+        loop.close()
+    for l in res["ref"][1]:
+        a, b = res["ref"][1][l], res["new"][1][l]
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), "level %d: max diff %g" % (l, np.abs(a - b).max())
+    assert np.array_equal(res["ref"][0], res["new"][0])
+    assert np.array_equal(res["ref"][2], res["new"][2])            # second frame (state carried over)
+    assert np.array_equal(res["ref"][3].view(np.uint32), res["new"][3].view(np.uint32))
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref/libref.so not built")
+def test_effects_and_image_ops_ab_reference():
+    from realtimedepthdiffusion_b200 import _native
+    rows, cols = 203, 317
+    bgr, gray, depth = effect_inputs(rows, cols, 33)
+    o, g, d = to_dev(bgr, 3), to_dev(gray), to_dev(depth)
+    outs = {}
+    for tag, api in (("ref", ob.ref_api()), ("new", _native.shims)):
+        r = []
+        for name in ("GPUSimulateDesaturation", "GPUSimulateHaze", "GPUSimulateDefocus"):
+            out = to_dev(np.zeros_like(bgr), 3)
+            torch.cuda.synchronize()
+            if name == "GPUSimulateDesaturation":
+                api[name](ptr(o), pitch(o), ptr(g), pitch(g), ptr(d), pitch(d), ptr(out), pitch(out), rows, cols)
+            else:
+                api[name](ptr(o), pitch(o), ptr(d), pitch(d), ptr(out), pitch(out), rows, cols)
+            torch.cuda.synchronize()
+            r.append(to_host(out, 3))
+        e0, s0 = to_dev(bgr, 3), to_dev(np.zeros((rows, cols), np.uint8))
+        api["GPUPaintImage"](100, 50, 192, 9, ptr(e0), pitch(e0), ptr(s0), pitch(s0), rows, cols)
+        api["GPUPaintImage"](2, 200, 64, 14, ptr(e0), pitch(e0), ptr(s0), pitch(s0), rows, cols)
+        torch.cuda.synchronize()
+        r += [to_host(e0, 3), to_host(s0)]
+        outs[tag] = r
+    for a, b in zip(outs["ref"], outs["new"]):
+        assert np.array_equal(a, b)
+
+
+# ---- whole-frame entry point -------------------------------------------------------------------
+
+@pytest.mark.parametrize("rows,cols,iters", [(203, 317, 120), (96, 130, 64), (360, 640, 100)])
+def test_frame_solve_host_vs_oracle(rtdd, rows, cols, iters):
+    bgr, scribble, edited = synth.synth_case(rows, cols, 77)
+    st = ob.FrameState(bgr)
+    want = st.solve(scribble, edited, iters)
+    ctx = rtdd.DepthDiffusion(rows, cols)
+    assert ctx.levels == st.levels
+    ctx.frame_set_image(bgr)
+    got = ctx.frame_solve_host(scribble, edited, iters, np.zeros((rows, cols), np.uint8)).numpy()
+    assert np.array_equal(got, want)
+    assert np.array_equal(ctx.frame_plane(ctx.PLANE_DEPTH, 0).cpu().numpy().view(np.uint32), st.depth[0].view(np.uint32))
+    # second frame: paint on the device, solve without any host traffic, compare with the oracle's replay
+    ev = synth.brush_events(rows, cols, 5, 1, 5)
+    for e in ev:
+        ctx.frame_paint(*e)
+    s2, e2 = synth.paint_events(bgr, ev, scribble.copy(), edited.copy())
+    want2 = st.solve(s2, e2, iters)
+    ctx.frame_solve(iters)
+    ctx.sync()
+    assert np.array_equal(ctx.frame_plane(ctx.PLANE_DEPTH_U8, 0).cpu().numpy(), want2)
+    ctx.close()
+
+
+# ---- golden vectors recorded from the reference on a B200 ---------------------------------------
+
+@pytest.mark.parametrize("name", ["synth_tiny", "synth_small", "synth_odd", "dog"])
+def test_shims_reproduce_reference_golden(name):
+    path = os.path.join(GOLD, "ref_solver_%s.npz" % name)
+    if not os.path.exists(path):
+        pytest.skip("golden %s missing" % path)
+    from realtimedepthdiffusion_b200 import _native
+    from tests.test_oracle_cpu import _load_case
+    z = np.load(path)
+    bgr, scribble, edited = _load_case(name)
+    loop = MainLoop(_native.shims, bgr)
+    u8 = loop.frame(scribble, edited, int(z["max_iterations"]), keep_levels=True)
+    for l, d in loop.per_level.items():
+        assert sha(d["out"]) == str(z["out_sha_%d" % l]), "level %d" % l
+    assert np.array_equal(u8, z["depth_u8"])
+    loop.close()
+
+
+# ---- full-size, size-independent properties (BASELINE configs 2 and 3) ---------------------------
+
+@pytest.mark.parametrize("rows,cols", [(1080, 1920), (2160, 3840)])
+def test_full_size_variants_agree_and_dirichlet_holds(rtdd, rows, cols):
+    bgr, scribble, edited = synth.synth_case(rows, cols, 1003)
+    outs = []
+    for variant, T in ((1, 0), (2, 8), (0, 0)):
+        ctx = rtdd.DepthDiffusion(rows, cols)
+        ctx.set_sweep_variant(variant, T)
+        ctx.frame_set_image(bgr)
+        u8 = ctx.frame_solve_host(scribble, edited, 1000, np.zeros((rows, cols), np.uint8)).numpy()
+        outs.append((u8, ctx.frame_plane(ctx.PLANE_DEPTH, 0).cpu().numpy()))
+        ctx.close()
+    for u8, f in outs[1:]:
+        assert np.array_equal(f.view(np.uint32), outs[0][1].view(np.uint32))
+        assert np.array_equal(u8, outs[0][0])
+    u8, f = outs[0]
+    m = scribble == 255
+    assert np.array_equal(f[m], edited[..., 0][m].astype(np.float32))       # Dirichlet pixels untouched
+    assert np.isfinite(f).all() and f.min() >= -1.0 and f.max() <= 256.0
+    # level-0 check against the oracle on a crop-independent property: one more oracle sweep count would be
+    # minutes of CPU at this size, so compare a full oracle solve of the coarsest two levels only (done in the
+    # small-size tests) and here assert idempotence of the Dirichlet injection + determinism across runs.
+    ctx = rtdd.DepthDiffusion(rows, cols)
+    ctx.frame_set_image(bgr)
+    u8b = ctx.frame_solve_host(scribble, edited, 1000, np.zeros((rows, cols), np.uint8)).numpy()
+    assert np.array_equal(u8b, u8)
+    ctx.close()
