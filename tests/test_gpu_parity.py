@@ -209,7 +209,8 @@ def effect_inputs(rows, cols, seed):
     yy, xx = np.mgrid[0:rows, 0:cols]
     depth = (255.0 * (0.5 + 0.5 * np.sin(xx / 37.0) * np.cos(yy / 23.0))).astype(np.float32)
     depth += rng.uniform(-0.5, 0.5, depth.shape).astype(np.float32)
-    depth[0, :5] = [0.0, -7.0, 255.0, 262.5, 1.0]
+    special = np.array([0.0, -7.0, 255.0, 262.5, 1.0], np.float32)
+    depth[0, : min(cols, 5)] = special[: min(cols, 5)]
     return bgr, gray, depth
 
 

@@ -196,3 +196,22 @@ def test_oracle_reproduces_reference_effects_golden():
         # haze: libdevice expf vs glibc expf -- at most one grey level on a tiny fraction of values
         h = ob.haze(bgr, depth).astype(np.int16) - z["GPUSimulateHaze"].astype(np.int16)
         assert np.abs(h).max() <= 1 and (h != 0).mean() < 1e-3
+
+
+def test_oracle_reproduces_reference_effects_on_dog():
+    """Config 1 end to end on the CPU: oracle solve of Dog (bit-exact, sha-pinned) then the three effects."""
+    path = os.path.join(GOLD, "ref_effects_dog.npz")
+    if not os.path.exists(path):
+        pytest.skip("golden missing")
+    z = np.load(path)
+    bgr, scribble, edited = _load_case("dog")
+    st = ob.FrameState(bgr)
+    st.solve(scribble, edited, 1000)
+    st.solve(*synth.paint_events(bgr, synth.brush_events(st.rows, st.cols, 99, 1, 6), scribble.copy(), edited.copy()), 1000)
+    depth = st.depth[0]
+    assert sha(depth) == str(z["depth_sha"])
+    gray = ob.bgr2gray(bgr)
+    assert sha(ob.desaturate(bgr, gray, depth)) == str(z["desaturation_sha"])
+    assert sha(ob.defocus(bgr, depth)) == str(z["defocus_sha"])
+    h = ob.haze(bgr, depth)[::4, ::4].astype(np.int16) - z["haze_sample"].astype(np.int16)
+    assert np.abs(h).max() <= 1 and (h != 0).mean() < 1e-3
