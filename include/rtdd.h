@@ -94,6 +94,12 @@ int rtdd_edge_weights(rtdd_ctx *ctx, const float *depth, size_t depthPitch,
  * the number of kernel launches it took. */
 int rtdd_level_sweep_ms(rtdd_ctx *ctx, int level, float *ms, int *iterations, int *kernels);
 
+/* Self-test of the sweep kernels' branch-free division (csrc/solver_kernels.cu: div_fast) against the
+ * compiler's IEEE div.rn (the operation the reference's `sum / count` compiles to, ref: src/GPUSolver.cu:104)
+ * on n counter-generated operand pairs.  mode 0 = the whole admitted range, 1 = the sweep's typical range,
+ * 2 = quotients placed next to rounding boundaries.  *mismatches (HOST) must come back 0. */
+int rtdd_selftest_division(rtdd_ctx *ctx, unsigned long long n, unsigned long long seed, int mode, unsigned long long *mismatches);
+
 /* Sweep implementation selector for rtdd_solve_level: 0 = auto (default),
  * 1 = one sweep per launch, 2 = temporally blocked tiles.  All variants are
  * bit-identical by construction; the selector exists for tests and profiling. */

@@ -125,6 +125,11 @@ class DepthDiffusion:
         self._ck(lib.rtdd_level_sweep_ms(self._h, int(level), C.byref(ms), C.byref(it), C.byref(k)))
         return ms.value, it.value, k.value
 
+    def selftest_division(self, n, seed=1, mode=0):
+        mism = C.c_ulonglong(0)
+        self._ck(lib.rtdd_selftest_division(self._h, int(n), int(seed), int(mode), C.byref(mism)))
+        return mism.value
+
     def edge_weights(self, depth, gray, level):
         rows, cols = depth.shape
         right = pitched_empty(rows, cols, torch.uint8, self.device)

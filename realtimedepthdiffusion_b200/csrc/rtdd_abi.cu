@@ -334,6 +334,22 @@ int rtdd_solve_level(rtdd_ctx *ctx, float *depth, size_t depthPitch, const uint8
     return 0;
 }
 
+int rtdd_selftest_division(rtdd_ctx *ctx, unsigned long long n, unsigned long long seed, int mode, unsigned long long *mismatches)
+{
+    if (!ctx) return RTDD_E_ARG;
+    if (!mismatches || mode < 0 || mode > 2) return rtdd_fail(ctx, RTDD_E_ARG, "rtdd_selftest_division");
+    DeviceGuard guard(ctx->device);
+    unsigned long long *d = nullptr;
+    RTDD_TRY(cudaMalloc((void **)&d, sizeof(*d)), "rtdd_selftest_division");
+    cudaError_t e = cudaMemsetAsync(d, 0, sizeof(*d), ctx->stream);
+    if (e == cudaSuccess) e = rtdd::launch_division_selftest(ctx->stream, n, seed, mode, d);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(mismatches, d, sizeof(*d), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    ctx->launches++;
+    return rtdd_check(ctx, e, "rtdd_selftest_division");
+}
+
 int rtdd_level_sweep_ms(rtdd_ctx *ctx, int level, float *ms, int *iterations, int *kernels)
 {
     if (!ctx) return RTDD_E_ARG;

@@ -103,6 +103,7 @@ struct OmegaPack { float w[RTDD_MAX_T]; };
 cudaError_t launch_sweep_blocked(cudaStream_t s, const RtddLevel &L, const float *lut, const float *x, const float *prev,
                                  float *xOut, float *prevOut, OmegaPack om, int T, int nsweeps, float gamma, bool firstSweep, int smCount);
 int blocked_max_T();
+cudaError_t launch_division_selftest(cudaStream_t s, unsigned long long n, unsigned long long seed, int mode, unsigned long long *dMismatches);
 cudaError_t launch_copy_out(cudaStream_t s, const RtddLevel &L, const float *x, float *depth, size_t depthPitch);
 cudaError_t launch_export_links(cudaStream_t s, const RtddLevel &L, uint8_t *linkRight, uint8_t *linkDown, size_t outPitch);
 

@@ -126,6 +126,33 @@ def test_edge_weight_pass_vs_oracle(rtdd, rows, cols, level, levels):
     ctx.close()
 
 
+def test_branch_free_division_matches_ieee_division(rtdd):
+    ctx = rtdd.DepthDiffusion(8, 8, 1)
+    for mode in (0, 1, 2):
+        assert ctx.selftest_division(1 << 31, seed=12345 + mode, mode=mode) == 0, mode
+    ctx.close()
+
+
+def test_slow_path_inputs_denormal_and_huge_depths(rtdd):
+    """Operands outside div_fast's range (denormal / huge / NaN-free extreme depths) take the IEEE fallback."""
+    rows, cols = 66, 140
+    gray, depth, scribble = random_level(rows, cols, 31, scribble_frac=0.05)
+    depth[10:20, 10:40] = 1e-39           # denormal depths -> denormal numerators
+    depth[30:34, 50:90] = 0.0
+    depth[40:44, 20:60] = 3.0e6           # beyond the 4096 load bound
+    depth[50, 100] = -2.5e4
+    for level, levels in ((0, 1), (0, 2)):
+        want = ob.solve_level(depth, scribble, gray, 21, level, levels - 1)
+        for variant, T in ((1, 0), (2, 8)):
+            ctx = rtdd.DepthDiffusion(rows, cols, levels)
+            ctx.set_sweep_variant(variant, T)
+            d, s, g = to_dev(depth), to_dev(scribble), to_dev(gray)
+            ctx.matrix_free_solver(d, s, g, 21, level)
+            ctx.sync()
+            assert np.array_equal(to_host(d).view(np.uint32), want.view(np.uint32)), (level, variant)
+            ctx.close()
+
+
 def test_call_order_and_argument_errors(rtdd):
     ctx = rtdd.DepthDiffusion(64, 64, 1, beta=None)
     d, s, g = to_dev(np.zeros((64, 64), np.float32)), to_dev(np.zeros((64, 64), np.uint8)), to_dev(np.zeros((64, 64), np.uint8))
