@@ -101,7 +101,8 @@ int rtdd_level_sweep_ms(rtdd_ctx *ctx, int level, float *ms, int *iterations, in
 int rtdd_selftest_division(rtdd_ctx *ctx, unsigned long long n, unsigned long long seed, int mode, unsigned long long *mismatches);
 
 /* Sweep implementation selector for rtdd_solve_level: 0 = auto (default),
- * 1 = one sweep per launch, 2 = temporally blocked tiles.  All variants are
+ * 1 = one sweep per launch, 2 = temporally blocked tiles, 3 = cluster-resident (whole level in the
+ * registers of one thread-block cluster for all sweeps; falls back to 2 if the level is too large).  All variants are
  * bit-identical by construction; the selector exists for tests and profiling. */
 int rtdd_set_sweep_variant(rtdd_ctx *ctx, int variant, int sweepsPerPass);
 

@@ -72,8 +72,13 @@ void destroy_graphs(rtdd_ctx *ctx)
 void pick_variant(const rtdd_ctx *ctx, const RtddLevel &L, int iters, int *variant, int *T)
 {
     int v = ctx->variant, t = ctx->sweepsPerPass;
-    if (v == 0) v = 2;
-    if (v == 2) {
+    int rR, rC, rB, rW;
+    const bool fits = rtdd::resident_plan(L.rows, L.cols, &rR, &rC, &rB, &rW);
+    if (v == 3 && !fits) v = 2;          // level too large for one cluster: temporally blocked instead
+    if (v == 0) v = (fits && iters >= 8) ? 3 : 2;
+    if (v == 3) {
+        t = 0;
+    } else if (v == 2) {
         if (t <= 0) {
             const long px = (long)L.rows * L.cols;
             t = (px >= (1L << 20)) ? 8 : 12;
@@ -101,6 +106,22 @@ int get_sweep_graph(rtdd_ctx *ctx, int level, int iters, RtddGraph **out)
     std::vector<float> om;
     omega_schedule(iters, om);
     const float gamma = 0.99f;
+    if (variant == 3 && iters > ctx->dOmegaCap) {
+        // the schedule is prefix-stable: keep one device copy long enough for the longest level seen
+        const int cap = iters > 4096 ? iters : 4096;
+        std::vector<float> all;
+        omega_schedule(cap, all);
+        float *d = nullptr;
+        RTDD_TRY(cudaMalloc((void **)&d, (size_t)cap * sizeof(float)), "omega table");
+        RTDD_TRY(cudaMemcpy(d, all.data(), (size_t)cap * sizeof(float), cudaMemcpyHostToDevice), "omega table");
+        if (ctx->dOmega) {
+            RTDD_TRY(cudaDeviceSynchronize(), "omega table");
+            destroy_graphs(ctx);         // graphs captured with the old table
+            cudaFree(ctx->dOmega);
+        }
+        ctx->dOmega = d;
+        ctx->dOmegaCap = cap;
+    }
 
     RtddGraph g;
     cudaGraph_t graph = nullptr;
@@ -108,7 +129,11 @@ int get_sweep_graph(rtdd_ctx *ctx, int level, int iters, RtddGraph **out)
     RTDD_TRY(cudaStreamBeginCapture(cs, cudaStreamCaptureModeRelaxed), "cudaStreamBeginCapture");
     cudaError_t e = cudaSuccess;
     int kernels = 0, result = 0;
-    if (variant == 1) {
+    if (variant == 3) {
+        e = rtdd::launch_sweep_resident(cs, L, ctx->dLut, L.x[0], L.x[2], ctx->dOmega, iters, gamma);
+        kernels = 1;
+        result = 2;
+    } else if (variant == 1) {
         // three-plane rotation: x_k in plane k%3, x_{k+1} -> (k+1)%3, x_{k-1} in (k+2)%3
         for (int k = 0; k < iters && e == cudaSuccess; k++) {
             e = rtdd::launch_sweep_single(cs, L, ctx->dLut, L.x[k % 3], L.x[(k + 2) % 3], L.x[(k + 1) % 3], om[k], gamma, k == 0);
@@ -240,6 +265,7 @@ int rtdd_destroy(rtdd_ctx *ctx)
         if (L.evBegin) cudaEventDestroy(L.evBegin);
         if (L.evEnd) cudaEventDestroy(L.evEnd);
     }
+    if (ctx->dOmega) cudaFree(ctx->dOmega);
     if (ctx->arena) cudaFree(ctx->arena);
     if (ctx->frameArena) cudaFree(ctx->frameArena);
     if (ctx->satScratch) cudaFree(ctx->satScratch);
@@ -284,7 +310,7 @@ int rtdd_levels(const rtdd_ctx *ctx) { return ctx ? ctx->levels : 0; }
 
 int rtdd_set_sweep_variant(rtdd_ctx *ctx, int variant, int sweepsPerPass)
 {
-    if (!ctx || variant < 0 || variant > 2 || sweepsPerPass < 0 || sweepsPerPass > RTDD_MAX_T) return rtdd_fail(ctx, RTDD_E_ARG, "rtdd_set_sweep_variant");
+    if (!ctx || variant < 0 || variant > 3 || sweepsPerPass < 0 || sweepsPerPass > RTDD_MAX_T) return rtdd_fail(ctx, RTDD_E_ARG, "rtdd_set_sweep_variant");
     ctx->variant = variant;
     ctx->sweepsPerPass = sweepsPerPass;
     return 0;

@@ -67,7 +67,9 @@ struct rtdd_ctx {
     float *dLut = nullptr;       // 257 floats
     float hLut[257];
     bool lutLoaded = false;
-    int variant = 0;             // 0 auto, 1 single-sweep, 2 temporally blocked
+    int variant = 0;             // 0 auto, 1 single-sweep, 2 temporally blocked, 3 cluster-resident
+    float *dOmega = nullptr;     // the omega schedule (prefix-stable), dOmegaCap entries
+    int dOmegaCap = 0;
     int sweepsPerPass = 0;       // 0 auto
     std::map<RtddGraphKey, RtddGraph> graphs;
     unsigned long long launches = 0;
@@ -103,6 +105,10 @@ struct OmegaPack { float w[RTDD_MAX_T]; };
 cudaError_t launch_sweep_blocked(cudaStream_t s, const RtddLevel &L, const float *lut, const float *x, const float *prev,
                                  float *xOut, float *prevOut, OmegaPack om, int T, int nsweeps, float gamma, bool firstSweep, int smCount);
 int blocked_max_T();
+// resident (one cluster, all sweeps in one launch); omegas = device array of nsweeps floats
+bool resident_plan(int rows, int cols, int *R, int *clusterSize, int *blocksPerCta, int *WX);
+cudaError_t launch_sweep_resident(cudaStream_t s, const RtddLevel &L, const float *lut, const float *x, float *xOut,
+                                  const float *omegas, int nsweeps, float gamma);
 cudaError_t launch_division_selftest(cudaStream_t s, unsigned long long n, unsigned long long seed, int mode, unsigned long long *dMismatches);
 cudaError_t launch_copy_out(cudaStream_t s, const RtddLevel &L, const float *x, float *depth, size_t depthPitch);
 cudaError_t launch_export_links(cudaStream_t s, const RtddLevel &L, uint8_t *linkRight, uint8_t *linkDown, size_t outPitch);

@@ -45,7 +45,7 @@ SIZES = [(1, 1), (1, 7), (9, 1), (2, 2), (16, 16), (17, 33), (67, 120), (135, 24
 
 
 @pytest.mark.parametrize("rows,cols", SIZES)
-@pytest.mark.parametrize("variant,T", [(1, 0), (2, 1), (2, 4), (2, 7), (2, 8), (2, 12), (2, 16), (0, 0)])
+@pytest.mark.parametrize("variant,T", [(1, 0), (2, 1), (2, 4), (2, 7), (2, 8), (2, 12), (2, 16), (3, 0), (0, 0)])
 def test_solve_level_bit_exact_vs_oracle(rtdd, rows, cols, variant, T):
     iters = 37
     for level, levels in ((0, 2), (1, 3), (2, 3)):
@@ -67,7 +67,7 @@ def test_iteration_counts_and_result_plane(rtdd, iters):
     rows, cols = 70, 150
     gray, depth, scribble = random_level(rows, cols, 5)
     want = ob.solve_level(depth, scribble, gray, iters, 0, 0)
-    for variant, T in ((1, 0), (2, 8), (2, 5)):
+    for variant, T in ((1, 0), (2, 8), (2, 5), (3, 0)):
         ctx = rtdd.DepthDiffusion(rows, cols, 1)
         ctx.set_sweep_variant(variant, T)
         d, s, g = to_dev(depth), to_dev(scribble), to_dev(gray)
@@ -143,7 +143,7 @@ def test_slow_path_inputs_denormal_and_huge_depths(rtdd):
     depth[50, 100] = -2.5e4
     for level, levels in ((0, 1), (0, 2)):
         want = ob.solve_level(depth, scribble, gray, 21, level, levels - 1)
-        for variant, T in ((1, 0), (2, 8)):
+        for variant, T in ((1, 0), (2, 8), (3, 0)):
             ctx = rtdd.DepthDiffusion(rows, cols, levels)
             ctx.set_sweep_variant(variant, T)
             d, s, g = to_dev(depth), to_dev(scribble), to_dev(gray)
@@ -380,7 +380,7 @@ def test_shims_reproduce_reference_golden(name):
 def test_full_size_variants_agree_and_dirichlet_holds(rtdd, rows, cols):
     bgr, scribble, edited = synth.synth_case(rows, cols, 1003)
     outs = []
-    for variant, T in ((1, 0), (2, 8), (0, 0)):
+    for variant, T in ((1, 0), (2, 8), (3, 0), (0, 0)):
         ctx = rtdd.DepthDiffusion(rows, cols)
         ctx.set_sweep_variant(variant, T)
         ctx.frame_set_image(bgr)
