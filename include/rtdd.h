@@ -105,6 +105,9 @@ int rtdd_selftest_division(rtdd_ctx *ctx, unsigned long long n, unsigned long lo
  * registers of one thread-block cluster for all sweeps; falls back to 2 if the level is too large).  All variants are
  * bit-identical by construction; the selector exists for tests and profiling. */
 int rtdd_set_sweep_variant(rtdd_ctx *ctx, int variant, int sweepsPerPass);
+/* Process-wide tuning knobs for experiments (tools/tune_blocked.py); results never change, only speed.
+ * "blocked_tile": 0 auto, 64 = 128x64-pixel regions, 32 = 128x32-pixel regions. */
+int rtdd_set_tuning(rtdd_ctx *ctx, const char *key, int value);
 
 /* ---- GPUImageProcessing -------------------------------------------------- */
 

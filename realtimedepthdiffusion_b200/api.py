@@ -109,6 +109,9 @@ class DepthDiffusion:
     def set_sweep_variant(self, variant, sweeps_per_pass=0):
         self._ck(lib.rtdd_set_sweep_variant(self._h, variant, sweeps_per_pass))
 
+    def set_tuning(self, key, value):
+        self._ck(lib.rtdd_set_tuning(self._h, key.encode(), int(value)))
+
     # -- GPUSolver -------------------------------------------------------------
     def load_weights(self, beta):
         self._ck(lib.rtdd_load_weights(self._h, beta))

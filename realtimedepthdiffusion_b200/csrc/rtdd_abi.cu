@@ -80,8 +80,10 @@ void pick_variant(const rtdd_ctx *ctx, const RtddLevel &L, int iters, int *varia
         t = 0;
     } else if (v == 2) {
         if (t <= 0) {
+            // measured on B200 (tools/tune_frame.py, 4K frame): 8 sweeps per HBM round trip for >= 1 M pixels,
+            // 12 for 256 K..1 M (128x64 tiles), 11 below (128x32 tiles)
             const long px = (long)L.rows * L.cols;
-            t = (px >= (1L << 20)) ? 8 : 12;
+            t = (px >= (1L << 20)) ? 8 : (px >= (1L << 18)) ? 12 : 11;
         }
         if (t > RTDD_MAX_T) t = RTDD_MAX_T;
         if (t > iters) t = iters > 0 ? iters : 1;
@@ -307,6 +309,19 @@ int rtdd_sync(rtdd_ctx *ctx)
 const char *rtdd_last_error(const rtdd_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 unsigned long long rtdd_launch_count(const rtdd_ctx *ctx) { return ctx ? ctx->launches : 0ULL; }
 int rtdd_levels(const rtdd_ctx *ctx) { return ctx ? ctx->levels : 0; }
+
+int rtdd_set_tuning(rtdd_ctx *ctx, const char *key, int value)
+{
+    if (!ctx || !key) return RTDD_E_ARG;
+    if (strcmp(key, "blocked_tile") == 0 && (value == 0 || value == 32 || value == 64)) {
+        rtdd::set_blocked_tile_override(value);
+        DeviceGuard guard(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+        destroy_graphs(ctx);
+        return 0;
+    }
+    return rtdd_fail(ctx, RTDD_E_ARG, "rtdd_set_tuning");
+}
 
 int rtdd_set_sweep_variant(rtdd_ctx *ctx, int variant, int sweepsPerPass)
 {
