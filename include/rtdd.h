@@ -109,6 +109,24 @@ int rtdd_set_sweep_variant(rtdd_ctx *ctx, int variant, int sweepsPerPass);
  * "blocked_tile": 0 auto, 64 = 128x64-pixel regions, 32 = 128x32-pixel regions. */
 int rtdd_set_tuning(rtdd_ctx *ctx, const char *key, int value);
 
+/* ---- row strips: one level of one very large image split across GPUs (BASELINE configs[4]) --------
+ * No reference counterpart (the reference is single-GPU); results are bit-identical to rtdd_solve_level.
+ * A rank keeps rows [winBegin, winEnd) of the level = its own rows plus H ghost rows on each side that is not an
+ * image edge.  rtdd_strip_init = the edge-weight pass on the window (ref: src/GPUSolver.cu:290-293);
+ * rtdd_strip_pass = nsweeps (<= haloT <= H) sweeps starting at sweep index firstSweep of the level's schedule
+ * (ref: src/GPUSolver.cu:295-309); afterwards the nsweeps rows next to a non-image window edge are stale and
+ * must be refreshed from the neighbouring rank before the next pass: rtdd_strip_planes returns the device
+ * planes holding x_k and x_{k-1} (row 0 = winBegin, row pitch pitchBytes) to send from / receive into;
+ * rtdd_strip_finish copies final rows [rowBegin, rowEnd) (level coordinates) into the pitched depth plane. */
+int rtdd_strip_init(rtdd_ctx *ctx, int level, const float *depth, size_t depthPitch, const uint8_t *scribble, size_t scribblePitch,
+                    const uint8_t *gray, size_t grayPitch, int rows, int cols, int winBegin, int winEnd);
+int rtdd_strip_pass(rtdd_ctx *ctx, int level, int firstSweep, int nsweeps, int haloT);
+int rtdd_strip_planes(rtdd_ctx *ctx, int level, float **xk, float **xkm1, size_t *pitchBytes, int *winBegin, int *winRows);
+int rtdd_strip_finish(rtdd_ctx *ctx, int level, float *depth, size_t depthPitch, int rowBegin, int rowEnd);
+/* cv::pyrUp restricted to destination rows [rowBegin, rowEnd); src and dst are the full planes */
+int rtdd_pyrup_depth_rows(rtdd_ctx *ctx, const float *src, size_t srcPitch, int srcRows, int srcCols,
+                          float *dst, size_t dstPitch, int dstRows, int dstCols, int rowBegin, int rowEnd);
+
 /* ---- GPUImageProcessing -------------------------------------------------- */
 
 /* replaces GPUConvertToFloat     ref: include/GPUImageProcessing.h:4-5, src/GPUImageProcessing.cu:8-21,72-79 */

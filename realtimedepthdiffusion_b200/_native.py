@@ -35,6 +35,11 @@ SIGNATURES = {
     "rtdd_edge_weights": (i32, [vp, vp, sz, vp, sz, i32, i32, i32, vp, vp, sz]),
     "rtdd_level_sweep_ms": (i32, [vp, i32, C.POINTER(f32), C.POINTER(i32), C.POINTER(i32)]),
     "rtdd_selftest_division": (i32, [vp, C.c_ulonglong, C.c_ulonglong, i32, C.POINTER(C.c_ulonglong)]),
+    "rtdd_strip_init": (i32, [vp, i32, vp, sz, vp, sz, vp, sz, i32, i32, i32, i32]),
+    "rtdd_strip_pass": (i32, [vp, i32, i32, i32, i32]),
+    "rtdd_strip_planes": (i32, [vp, i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(sz), C.POINTER(i32), C.POINTER(i32)]),
+    "rtdd_strip_finish": (i32, [vp, i32, vp, sz, i32, i32]),
+    "rtdd_pyrup_depth_rows": (i32, [vp, vp, sz, i32, i32, vp, sz, i32, i32, i32, i32]),
     "rtdd_set_tuning": (i32, [vp, C.c_char_p, i32]),
     "rtdd_set_sweep_variant": (i32, [vp, i32, i32]),
     "rtdd_convert_to_float": (i32, [vp, vp, sz, vp, sz, vp, sz, i32, i32]),

@@ -206,10 +206,10 @@ __device__ __forceinline__ float pyrup_h(const float *__restrict__ s, int n, int
 
 __global__ void __launch_bounds__(256)
 pyrup_depth_kernel(const float *__restrict__ src, size_t srcPitch, int srows, int scols,
-                   float *__restrict__ dst, size_t dstPitch, int drows, int dcols)
+                   float *__restrict__ dst, size_t dstPitch, int drows, int dcols, int dy0)
 {
     const int dx = blockIdx.x * blockDim.x + threadIdx.x;
-    int dy = blockIdx.y * blockDim.y + threadIdx.y;
+    int dy = dy0 + blockIdx.y * blockDim.y + threadIdx.y;   // rows [dy0, drows) of the destination
     if (dx >= dcols || dy >= drows) return;
     float *out = (float *)((char *)dst + (size_t)dy * dstPitch) + dx;
     if (dy >= 2 * srows) dy = 2 * srows - 2;               // odd destination height: repeat row 2n-2
@@ -232,9 +232,17 @@ pyrup_depth_kernel(const float *__restrict__ src, size_t srcPitch, int srows, in
 cudaError_t launch_pyrup_depth(cudaStream_t s, const float *src, size_t srcPitch, int srows, int scols,
                                float *dst, size_t dstPitch, int drows, int dcols)
 {
+    return launch_pyrup_depth_rows(s, src, srcPitch, srows, scols, dst, dstPitch, drows, dcols, 0, drows);
+}
+
+// rows [rowBegin, rowEnd) of the destination only (row-strip decomposition); src/dst are the full planes
+cudaError_t launch_pyrup_depth_rows(cudaStream_t s, const float *src, size_t srcPitch, int srows, int scols,
+                                    float *dst, size_t dstPitch, int drows, int dcols, int rowBegin, int rowEnd)
+{
+    if (rowEnd <= rowBegin) return cudaSuccess;
     dim3 block(64, 4);
-    dim3 grid(rtdd_div_up(dcols, block.x), rtdd_div_up(drows, block.y));
-    pyrup_depth_kernel<<<grid, block, 0, s>>>(src, srcPitch, srows, scols, dst, dstPitch, drows, dcols);
+    dim3 grid(rtdd_div_up(dcols, block.x), rtdd_div_up(rowEnd - rowBegin, block.y));
+    pyrup_depth_kernel<<<grid, block, 0, s>>>(src, srcPitch, srows, scols, dst, dstPitch, rowEnd, dcols, rowBegin);
     return cudaGetLastError();
 }
 

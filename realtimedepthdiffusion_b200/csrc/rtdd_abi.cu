@@ -420,6 +420,104 @@ int rtdd_edge_weights(rtdd_ctx *ctx, const float *depth, size_t depthPitch, cons
     return 0;
 }
 
+// ---- row strips (multi-GPU domain decomposition of one level) -----------------------
+//
+// A rank owns rows [a, b) of a level and keeps a window [a - H, b + H) (clipped to the image) in the level's
+// planes.  Window edges that are not image edges are treated like the inner edges of the blocked kernel's tiles:
+// after n sweeps the n rows next to such an edge are stale, so with H >= the sweeps between two halo exchanges
+// every owned row has gone through exactly the reference's per-pixel recipe -- bit-identical to one GPU.
+// The exchange itself (the (x_k, x_{k-1}) rows next to the strip boundary) is the caller's: NCCL send/recv on
+// rtdd_strip_planes' pointers (realtimedepthdiffusion_b200/strips.py).
+
+int rtdd_strip_init(rtdd_ctx *ctx, int level, const float *depth, size_t depthPitch, const uint8_t *scribble, size_t scribblePitch,
+                    const uint8_t *gray, size_t grayPitch, int rows, int cols, int winBegin, int winEnd)
+{
+    if (!ctx) return RTDD_E_ARG;
+    if (!ctx->lutLoaded) return rtdd_fail(ctx, RTDD_E_STATE, "rtdd_strip_init (rtdd_load_weights not called)");
+    if (!depth || !scribble || !gray || level < 0 || level >= ctx->levels) return rtdd_fail(ctx, RTDD_E_ARG, "rtdd_strip_init");
+    RtddLevel &L = ctx->lv[level];
+    if (rows != L.rows || cols != L.cols || winBegin < 0 || winEnd > rows || winEnd <= winBegin) return rtdd_fail(ctx, RTDD_E_ARG, "rtdd_strip_init");
+    DeviceGuard guard(ctx->device);
+    RtddLevel W = L;
+    W.rows = winEnd - winBegin;
+    const bool coarsest = (level == ctx->levels - 1);
+    const int threshold = (level == 0) ? 0 : 4;
+    const float *d = (const float *)((const char *)depth + (size_t)winBegin * depthPitch);
+    // the window's last row needs the gray/depth row below it only if that row is inside the window; a window edge
+    // inside the image simply loses that link, which only affects rows that go stale anyway
+    RTDD_TRY(rtdd::launch_level_init(ctx->stream, W, d, depthPitch, scribble + (size_t)winBegin * scribblePitch, scribblePitch,
+                                     gray + (size_t)winBegin * grayPitch, grayPitch, coarsest, threshold, L.x[0]), "rtdd_strip_init");
+    ctx->launches++;
+    L.stripBegin = winBegin; L.stripRows = W.rows; L.stripPair = 0;
+    return 0;
+}
+
+int rtdd_strip_pass(rtdd_ctx *ctx, int level, int firstSweep, int nsweeps, int haloT)
+{
+    if (!ctx) return RTDD_E_ARG;
+    if (level < 0 || level >= ctx->levels) return rtdd_fail(ctx, RTDD_E_ARG, "rtdd_strip_pass");
+    RtddLevel &L = ctx->lv[level];
+    if (L.stripRows <= 0) return rtdd_fail(ctx, RTDD_E_STATE, "rtdd_strip_pass (rtdd_strip_init not called)");
+    if (firstSweep < 0 || nsweeps < 1 || haloT < nsweeps || haloT > RTDD_MAX_T) return rtdd_fail(ctx, RTDD_E_ARG, "rtdd_strip_pass");
+    DeviceGuard guard(ctx->device);
+    std::vector<float> om;
+    omega_schedule(firstSweep + nsweeps, om);
+    rtdd::OmegaPack pack;
+    for (int i = 0; i < RTDD_MAX_T; i++) pack.w[i] = (i < nsweeps) ? om[firstSweep + i] : 0.0f;
+    RtddLevel W = L;
+    W.rows = L.stripRows;
+    const int src = L.stripPair, dst = src ^ 2;
+    RTDD_TRY(rtdd::launch_sweep_blocked(ctx->stream, W, ctx->dLut, L.x[src], L.x[src + 1], L.x[dst], L.x[dst + 1], pack, haloT, nsweeps, 0.99f,
+                                        firstSweep == 0, ctx->smCount), "rtdd_strip_pass");
+    ctx->launches++;
+    L.stripPair = dst;
+    return 0;
+}
+
+int rtdd_strip_planes(rtdd_ctx *ctx, int level, float **xk, float **xkm1, size_t *pitchBytes, int *winBegin, int *winRows)
+{
+    if (!ctx) return RTDD_E_ARG;
+    if (level < 0 || level >= ctx->levels) return rtdd_fail(ctx, RTDD_E_ARG, "rtdd_strip_planes");
+    RtddLevel &L = ctx->lv[level];
+    if (L.stripRows <= 0) return rtdd_fail(ctx, RTDD_E_STATE, "rtdd_strip_planes");
+    if (xk) *xk = L.x[L.stripPair];
+    if (xkm1) *xkm1 = L.x[L.stripPair + 1];
+    if (pitchBytes) *pitchBytes = (size_t)L.pitchF * sizeof(float);
+    if (winBegin) *winBegin = L.stripBegin;
+    if (winRows) *winRows = L.stripRows;
+    return 0;
+}
+
+int rtdd_strip_finish(rtdd_ctx *ctx, int level, float *depth, size_t depthPitch, int rowBegin, int rowEnd)
+{
+    if (!ctx) return RTDD_E_ARG;
+    if (!depth || level < 0 || level >= ctx->levels) return rtdd_fail(ctx, RTDD_E_ARG, "rtdd_strip_finish");
+    RtddLevel &L = ctx->lv[level];
+    if (L.stripRows <= 0 || rowBegin < L.stripBegin || rowEnd > L.stripBegin + L.stripRows || rowEnd <= rowBegin)
+        return rtdd_fail(ctx, RTDD_E_ARG, "rtdd_strip_finish");
+    DeviceGuard guard(ctx->device);
+    RtddLevel W = L;
+    W.rows = rowEnd - rowBegin;
+    const float *x = L.x[L.stripPair] + (size_t)(rowBegin - L.stripBegin) * L.pitchF;
+    RTDD_TRY(rtdd::launch_copy_out(ctx->stream, W, x, (float *)((char *)depth + (size_t)rowBegin * depthPitch), depthPitch), "rtdd_strip_finish");
+    ctx->launches++;
+    return 0;
+}
+
+int rtdd_pyrup_depth_rows(rtdd_ctx *ctx, const float *src, size_t srcPitch, int srcRows, int srcCols,
+                          float *dst, size_t dstPitch, int dstRows, int dstCols, int rowBegin, int rowEnd)
+{
+    if (!ctx) return RTDD_E_ARG;
+    if (!src || !dst || srcRows < 1 || srcCols < 1 || dstRows < 2 * srcRows || dstRows > 2 * srcRows + 1 ||
+        dstCols < 2 * srcCols || dstCols > 2 * srcCols + 1 || rowBegin < 0 || rowEnd > dstRows || rowEnd < rowBegin)
+        return rtdd_fail(ctx, RTDD_E_ARG, "rtdd_pyrup_depth_rows");
+    DeviceGuard guard(ctx->device);
+    RTDD_TRY(rtdd::launch_pyrup_depth_rows(ctx->stream, src, srcPitch, srcRows, srcCols, dst, dstPitch, dstRows, dstCols, rowBegin, rowEnd),
+             "rtdd_pyrup_depth_rows");
+    ctx->launches++;
+    return 0;
+}
+
 // ---- GPUImageProcessing --------------------------------------------------------
 
 int rtdd_convert_to_float(rtdd_ctx *ctx, const uint8_t *src, size_t srcPitch, float *dst, size_t dstPitch,

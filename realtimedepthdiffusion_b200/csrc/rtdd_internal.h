@@ -26,6 +26,8 @@ struct RtddLevel {
     cudaEvent_t evBegin = nullptr, evEnd = nullptr;
     bool timed = false;
     int lastIters = 0, lastKernels = 0;
+    // row-strip mode (rtdd_strip_*): the level's planes hold rows [stripBegin, stripBegin + stripRows) of the level
+    int stripBegin = 0, stripRows = 0, stripPair = 0;
 };
 
 // Context-owned images of the frame driver (what main.cpp keeps in GpuMat vectors).
@@ -127,6 +129,8 @@ cudaError_t launch_bgr2gray(cudaStream_t s, const uint8_t *bgr, size_t bgrPitch,
 cudaError_t launch_pyrdown_gray(cudaStream_t s, const uint8_t *src, size_t srcPitch, int srows, int scols, uint8_t *dst, size_t dstPitch);
 cudaError_t launch_pyrup_depth(cudaStream_t s, const float *src, size_t srcPitch, int srows, int scols,
                                float *dst, size_t dstPitch, int drows, int dcols);
+cudaError_t launch_pyrup_depth_rows(cudaStream_t s, const float *src, size_t srcPitch, int srows, int scols,
+                                    float *dst, size_t dstPitch, int drows, int dcols, int rowBegin, int rowEnd);
 cudaError_t launch_quantise(cudaStream_t s, const float *src, size_t srcPitch, uint8_t *dst, size_t dstPitch, int rows, int cols);
 cudaError_t launch_fill_f32(cudaStream_t s, float *dst, size_t pitch, int rows, int cols, float v);
 

@@ -41,7 +41,7 @@ def random_level(rows, cols, seed, scribble_frac=0.1):
 
 
 SIZES = [(1, 1), (1, 7), (9, 1), (2, 2), (16, 16), (17, 33), (67, 120), (135, 240), (64, 128), (65, 129),
-         (100, 257), (203, 317), (270, 480)]
+         (100, 257), (203, 317), (270, 480), (256, 256), (100, 300), (600, 100), (64, 64)]
 
 
 @pytest.mark.parametrize("rows,cols", SIZES)
@@ -402,3 +402,35 @@ def test_full_size_variants_agree_and_dirichlet_holds(rtdd, rows, cols):
     u8b = ctx.frame_solve_host(scribble, edited, 1000, np.zeros((rows, cols), np.uint8)).numpy()
     assert np.array_equal(u8b, u8)
     ctx.close()
+
+
+# ---- row strips (multi-GPU domain decomposition), emulated on one GPU --------------------------------
+
+@pytest.mark.parametrize("rows,cols,nranks,halo,iters", [(512, 640, 2, 8, 150), (700, 333, 3, 8, 90), (1080, 1920, 4, 8, 1000), (401, 260, 2, 5, 64)])
+def test_strip_decomposition_on_one_gpu_is_bit_identical(rtdd, rows, cols, nranks, halo, iters):
+    """Several ranks' worth of strip contexts on ONE device, driven in lockstep with device-to-device halo copies:
+    the same coroutine and the same rtdd_strip_* entry points the NCCL path uses."""
+    from realtimedepthdiffusion_b200 import strips
+    bgr, scribble, edited = synth.synth_case(rows, cols, 4242)
+    ref = rtdd.DepthDiffusion(rows, cols)
+    ref.frame_set_image(bgr)
+    want_u8 = ref.frame_solve_host(scribble, edited, iters, np.zeros((rows, cols), np.uint8)).numpy()
+    want = ref.frame_plane(ref.PLANE_DEPTH, 0).cpu().numpy()
+    ref.close()
+    engines = []
+    for r in range(nranks):
+        ctx = rtdd.DepthDiffusion(rows, cols)
+        engines.append(strips.GpuStripEngine(ctx, to_dev(bgr, 3), to_dev(scribble), to_dev(edited, 3)))
+    results, exchanges = strips.run_local(engines, iters, halo=halo, min_strip_pixels=1)
+    torch.cuda.synchronize()
+    assert exchanges > 0
+    got = np.zeros_like(want)
+    got_u8 = np.zeros_like(want_u8)
+    for r, (plan, own) in enumerate(results):
+        assert plan[0] is not None and plan[0][r] == own
+        got[own[0]:own[1]] = to_host(engines[r].depth[0])[own[0]:own[1]]
+        got_u8[own[0]:own[1]] = to_host(engines[r].depth_u8)[own[0]:own[1]]
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), "max diff %g" % np.abs(got - want).max()
+    assert np.array_equal(got_u8, want_u8)
+    for e in engines:
+        e.ctx.close()

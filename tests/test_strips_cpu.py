@@ -1,0 +1,104 @@
+"""Row-strip decomposition on the CPU: planning, lockstep emulation, and a real world_size-2 gloo run.
+The arithmetic is the oracle's; what is under test is realtimedepthdiffusion_b200/strips.py."""
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import binding as ob
+from realtimedepthdiffusion_b200 import strips, synth
+from tests.strip_cpu_engine import CpuStripEngine
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_plan_strips_geometry():
+    sizes = [(16384 >> l, 16384 >> l) for l in range(9)]
+    for n in (2, 4, 8):
+        plan = strips.plan_strips(sizes, n, 8)
+        split = [l for l in range(9) if plan[l] is not None]
+        assert split == [0, 1, 2, 3]                      # >= 4 M pixels
+        for l in split:
+            rows = sizes[l][0]
+            assert plan[l][0][0] == 0 and plan[l][-1][1] == rows
+            for r in range(n - 1):
+                assert plan[l][r][1] == plan[l][r + 1][0]
+            if l > 0 and plan[l - 1] is not None:
+                for r in range(n):
+                    assert plan[l - 1][r][0] == 2 * plan[l][r][0]
+    assert all(p is None for p in strips.plan_strips(sizes, 1, 8))
+    # odd sizes: the last strip absorbs the extra row
+    sizes = [(1081, 700), (540, 350), (270, 175)]
+    plan = strips.plan_strips(sizes, 3, 4, min_strip_pixels=1)
+    assert plan[0][-1][1] == 1081 and plan[1][-1][1] == 540 and plan[2][-1][1] == 270
+    assert plan[0][1][0] == 2 * plan[1][1][0] == 4 * plan[2][1][0]
+
+
+@pytest.mark.parametrize("rows,cols,nranks,halo,iters", [(203, 150, 2, 4, 70), (256, 96, 3, 8, 100), (181, 130, 2, 5, 33)])
+def test_lockstep_strips_are_bit_identical_to_the_single_solve(rows, cols, nranks, halo, iters):
+    bgr, scribble, edited = synth.synth_case(rows, cols, 321)
+    want_state = ob.FrameState(bgr)
+    want = want_state.solve(scribble, edited, iters)
+    engines = [CpuStripEngine(bgr, scribble, edited) for _ in range(nranks)]
+    results, exchanges = strips.run_local(engines, iters, halo=halo, min_strip_pixels=1)
+    assert exchanges > 0
+    got = np.zeros_like(want)
+    gotf = np.zeros_like(want_state.depth[0])
+    for r, (plan, own) in enumerate(results):
+        assert plan[0] is not None
+        got[own[0]:own[1]] = engines[r].depth_u8[own[0]:own[1]]
+        gotf[own[0]:own[1]] = engines[r].st.depth[0][own[0]:own[1]]
+    assert np.array_equal(gotf.view(np.uint32), want_state.depth[0].view(np.uint32))
+    assert np.array_equal(got, want)
+
+
+WORKER = r'''
+import os, sys
+sys.path.insert(0, %(root)r)
+import numpy as np, torch, torch.distributed as dist
+from oracle import binding as ob
+from realtimedepthdiffusion_b200 import strips, synth
+from tests.strip_cpu_engine import CpuStripEngine
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+ob.set_num_threads(2)
+rows, cols, iters, halo = 203, 150, 70, 4
+bgr, scribble, edited = synth.synth_case(rows, cols, 321)
+eng = CpuStripEngine(bgr, scribble, edited)
+plan, own, exchanges = strips.run_distributed(eng, dist, iters, halo=halo, min_strip_pixels=1)
+full = torch.zeros((rows, cols), dtype=torch.float32)
+full[own[0]:own[1]] = torch.from_numpy(eng.st.depth[0][own[0]:own[1]])
+dist.all_reduce(full)                      # disjoint rows: the sum assembles the image
+if rank == 0:
+    st = ob.FrameState(bgr)
+    st.solve(scribble, edited, iters)
+    ok = np.array_equal(full.numpy().view(np.uint32), st.depth[0].view(np.uint32))
+    print("STRIPS_OK" if ok and exchanges > 0 else "STRIPS_MISMATCH", exchanges, flush=True)
+dist.destroy_process_group()
+'''
+
+
+def test_world_size_2_gloo_strips_match_single_solve(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER % {"root": ROOT})
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), str(script)]
+    env = dict(os.environ, OMP_NUM_THREADS="2")
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=280, env=env, cwd=ROOT)
+    assert "STRIPS_OK" in r.stdout, r.stdout[-3000:]
+
+
+def test_batch_sharding_is_a_partition():
+    """configs[3]: image i -> rank i mod N, every image exactly once."""
+    for n in (1, 2, 4, 8):
+        seen = []
+        for rank in range(n):
+            seen += list(range(rank, 256, n))
+        assert sorted(seen) == list(range(256))

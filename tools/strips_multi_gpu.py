@@ -1,0 +1,156 @@
+"""Row-strip solve of one large image on N GPUs (torchrun, NCCL) -- BASELINE configs[4].
+
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+      tools/strips_multi_gpu.py --size 16384 --steps 5 [--check]
+
+Prints one JSON line from rank 0: ms per full-pyramid solve (max over ranks, CUDA events), ms of the split levels alone,
+and with --check (sizes up to 4096) the bit-for-bit comparison with the single-GPU solve."""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import realtimedepthdiffusion_b200 as rtdd                      # noqa: E402
+from realtimedepthdiffusion_b200 import strips, synth          # noqa: E402
+from realtimedepthdiffusion_b200.api import pitched_empty     # noqa: E402
+
+
+def synth_on_device(rows, cols, seed, ctx, coverage=0.10):
+    """Counter-seeded synthetic image + brush scribbles generated ON the device (identical on every rank)."""
+    dev = ctx.device
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    rng = np.random.default_rng(seed)
+    bgr = pitched_empty(rows, cols, torch.uint8, dev, channels=3)
+    img = bgr.view(torch.uint8)
+    base = rng.integers(0, 256, 3)
+    v = img[:, : cols * 3].view(rows, cols, 3) if img.stride(0) == cols * 3 else None
+    plane = torch.empty((rows, cols, 3), dtype=torch.uint8, device=dev)
+    plane[:] = torch.tensor(base, dtype=torch.uint8, device=dev)
+    for _ in range(64):
+        cy, cx = rng.uniform(0, rows), rng.uniform(0, cols)
+        hy, hx = rng.uniform(0.03, 0.25) * rows, rng.uniform(0.03, 0.25) * cols
+        colour = torch.tensor(rng.integers(0, 256, 3), dtype=torch.uint8, device=dev)
+        y0, y1 = max(int(cy - hy), 0), min(int(cy + hy) + 1, rows)
+        x0, x1 = max(int(cx - hx), 0), min(int(cx + hx) + 1, cols)
+        if y1 <= y0 or x1 <= x0:
+            continue
+        if rng.random() < 0.5:
+            plane[y0:y1, x0:x1] = colour
+        else:
+            yy = (torch.arange(y0, y1, device=dev, dtype=torch.float32)[:, None] - cy) / hy
+            xx = (torch.arange(x0, x1, device=dev, dtype=torch.float32)[None, :] - cx) / hx
+            m = (yy * yy + xx * xx) <= 1.0
+            sub = plane[y0:y1, x0:x1]
+            sub[m] = colour
+    step = max(1, (1 << 24) // cols)
+    for r0 in range(0, rows, step):                             # noise in row chunks (bounded temporaries)
+        r1 = min(rows, r0 + step)
+        n = torch.randn((r1 - r0, cols, 1), generator=g, device=dev) * 4.0
+        plane[r0:r1] = (plane[r0:r1].float() + n).round_().clamp_(0, 255).to(torch.uint8)
+    bgr.copy_(plane.view(rows, cols * 3))
+    del plane
+    scribble = pitched_empty(rows, cols, torch.uint8, dev, fill=0)
+    edited = pitched_empty(rows, cols, torch.uint8, dev, channels=3)
+    edited.copy_(bgr)
+    radius = int(min(rows, cols) * 0.02)
+    side = 2 * (radius // 2) + 1
+    per_stroke = side * side + 23 * side * max(radius * 0.6, 1.0)
+    nstrokes = max(int(coverage * rows * cols / per_stroke), 2)
+    for (x, y, colour, rad) in synth.brush_events(rows, cols, seed, nstrokes, 24):
+        ctx.paint_image(x, y, colour, rad, edited, scribble)    # the reference's brush (GPUPaintImage)
+    ctx.sync()
+    return bgr, scribble, edited
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--size", type=int, default=16384)
+    ap.add_argument("--rows", type=int, default=0)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=2)
+    ap.add_argument("--halo", type=int, default=8)
+    ap.add_argument("--min-strip-pixels", type=int, default=1 << 22)
+    ap.add_argument("--check", action="store_true")
+    args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rank = dist.get_rank() if world > 1 else 0
+    rows, cols = (args.rows or args.size), args.size
+    ctx = rtdd.DepthDiffusion(rows, cols)
+    stream = torch.cuda.Stream()
+    ctx.set_stream(stream)
+    with torch.cuda.stream(stream):
+        bgr, scribble, edited = synth_on_device(rows, cols, 1005, ctx)
+        eng = strips.GpuStripEngine(ctx, bgr, scribble, edited)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+        def frame():
+            for d in eng.depth:
+                d.fill_(255.0)                                   # first-frame state (main.cpp:136), outside the timed region
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            ev0.record(stream)
+            if world > 1:
+                plan, own, exchanges = strips.run_distributed(eng, dist, 1000, halo=args.halo, min_strip_pixels=args.min_strip_pixels)
+            else:
+                res, exchanges = strips.run_local([eng], 1000, halo=args.halo, min_strip_pixels=args.min_strip_pixels)
+                plan, own = res[0]
+            ev1.record(stream)
+            torch.cuda.synchronize()
+            return ev0.elapsed_time(ev1), plan, own, exchanges
+
+        for _ in range(args.warmup):
+            frame()
+        times = []
+        for _ in range(args.steps):
+            ms, plan, own, exchanges = frame()
+            times.append(ms)
+        ms = float(np.median(times))
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ok = None
+        if args.check:
+            solo = rtdd.DepthDiffusion(rows, cols)
+            solo.set_stream(stream)
+            e1 = strips.GpuStripEngine(solo, bgr, scribble.clone(), edited.clone())
+            strips.run_local([e1], 1000, halo=args.halo)
+            torch.cuda.synchronize()
+            mine = eng.depth[0][own[0]:own[1]]
+            ref = e1.depth[0][own[0]:own[1]]
+            same = torch.equal(mine.view(torch.int32), ref.view(torch.int32))
+            f = torch.tensor([1 if same else 0], device="cuda")
+            if world > 1:
+                dist.all_reduce(f, op=dist.ReduceOp.MIN)
+            ok = bool(f.item())
+    if rank == 0:
+        total = 0
+        L = ctx.levels
+        per = []
+        for l, (r, c) in enumerate(ctx.sizes):
+            it = strips.level_iterations(1000, L, l)
+            total += r * c * it
+            per.append({"level": l, "size": "%dx%d" % (c, r), "sweeps": it, "split": plan[l] is not None})
+        print(json.dumps({"workload": "configs[4]: %dx%d single synthetic image, row strips + NVLink halo exchange (NCCL send/recv), halo %d rows"
+                                      % (cols, rows, args.halo),
+                          "n_gpus": world, "ms_per_solve": float(t.item()), "Mpixel-sweeps/s": total / (float(t.item()) * 1e-3) / 1e6,
+                          "pixel_sweeps": total, "halo_exchanges_per_solve": exchanges, "levels": per, "scaling": "strong",
+                          "bit_identical_to_single_gpu": ok}), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
