@@ -94,81 +94,147 @@ void pick_variant(const rtdd_ctx *ctx, const RtddLevel &L, int iters, int *varia
     *T = t;
 }
 
-// Build (or fetch) the CUDA graph that runs `iters` sweeps on level `level`
-// starting from plane x[0] (prev = implicit zeros).
-int get_sweep_graph(rtdd_ctx *ctx, int level, int iters, RtddGraph **out)
+int ensure_omega_table(rtdd_ctx *ctx, int iters)
+{
+    if (iters <= ctx->dOmegaCap) return 0;
+    // the schedule is prefix-stable: keep one device copy long enough for the longest level seen
+    const int cap = iters > 4096 ? iters : 4096;
+    std::vector<float> all;
+    omega_schedule(cap, all);
+    float *d = nullptr;
+    RTDD_TRY(cudaMalloc((void **)&d, (size_t)cap * sizeof(float)), "omega table");
+    RTDD_TRY(cudaMemcpy(d, all.data(), (size_t)cap * sizeof(float), cudaMemcpyHostToDevice), "omega table");
+    if (ctx->dOmega) {
+        RTDD_TRY(cudaDeviceSynchronize(), "omega table");
+        destroy_graphs(ctx);         // graphs captured with the old table
+        cudaFree(ctx->dOmega);
+    }
+    ctx->dOmega = d;
+    ctx->dOmegaCap = cap;
+    return 0;
+}
+
+bool target_ok(const float *depth, size_t depthPitch)
+{
+    return (((uintptr_t)depth | depthPitch) & 15u) == 0;
+}
+
+// Enqueue `iters` sweeps of `level` on stream `s`, starting from plane x[0] (prev = implicit zeros).  The last
+// pass writes to *target when given (caller's depth plane / u8 map); otherwise *resultPlane tells where x_K is.
+int enqueue_sweeps(rtdd_ctx *ctx, cudaStream_t s, int level, int iters, const rtdd::SweepTarget *target, int *kernels, int *resultPlane)
 {
     const RtddLevel &L = ctx->lv[level];
     int variant, T;
     pick_variant(ctx, L, iters, &variant, &T);
-    const RtddGraphKey key{level, iters, variant, T};
-    auto it = ctx->graphs.find(key);
-    if (it != ctx->graphs.end()) { *out = &it->second; return 0; }
-
     std::vector<float> om;
     omega_schedule(iters, om);
     const float gamma = 0.99f;
-    if (variant == 3 && iters > ctx->dOmegaCap) {
-        // the schedule is prefix-stable: keep one device copy long enough for the longest level seen
-        const int cap = iters > 4096 ? iters : 4096;
-        std::vector<float> all;
-        omega_schedule(cap, all);
-        float *d = nullptr;
-        RTDD_TRY(cudaMalloc((void **)&d, (size_t)cap * sizeof(float)), "omega table");
-        RTDD_TRY(cudaMemcpy(d, all.data(), (size_t)cap * sizeof(float), cudaMemcpyHostToDevice), "omega table");
-        if (ctx->dOmega) {
-            RTDD_TRY(cudaDeviceSynchronize(), "omega table");
-            destroy_graphs(ctx);         // graphs captured with the old table
-            cudaFree(ctx->dOmega);
-        }
-        ctx->dOmega = d;
-        ctx->dOmegaCap = cap;
-    }
-
-    RtddGraph g;
-    cudaGraph_t graph = nullptr;
-    cudaStream_t cs = ctx->captureStream;
-    RTDD_TRY(cudaStreamBeginCapture(cs, cudaStreamCaptureModeRelaxed), "cudaStreamBeginCapture");
     cudaError_t e = cudaSuccess;
-    int kernels = 0, result = 0;
+    int n = 0, result = 0;
     if (variant == 3) {
-        e = rtdd::launch_sweep_resident(cs, L, ctx->dLut, L.x[0], L.x[2], ctx->dOmega, iters, gamma);
-        kernels = 1;
+        e = rtdd::launch_sweep_resident(s, L, ctx->dLut, L.x[0], L.x[2], ctx->dOmega, iters, gamma, target);
+        n = 1;
         result = 2;
     } else if (variant == 1) {
         // three-plane rotation: x_k in plane k%3, x_{k+1} -> (k+1)%3, x_{k-1} in (k+2)%3
         for (int k = 0; k < iters && e == cudaSuccess; k++) {
-            e = rtdd::launch_sweep_single(cs, L, ctx->dLut, L.x[k % 3], L.x[(k + 2) % 3], L.x[(k + 1) % 3], om[k], gamma, k == 0);
-            kernels++;
+            e = rtdd::launch_sweep_single(s, L, ctx->dLut, L.x[k % 3], L.x[(k + 2) % 3], L.x[(k + 1) % 3], om[k], gamma, k == 0,
+                                          (k == iters - 1) ? target : nullptr);
+            n++;
         }
         result = iters % 3;
     } else {
         // pair A = planes (0,1), pair B = planes (2,3); each pass reads one pair and writes the other
         int cur = 0;
         for (int k = 0; k < iters && e == cudaSuccess; k += T) {
-            const int n = (iters - k < T) ? iters - k : T;
+            const int m = (iters - k < T) ? iters - k : T;
             rtdd::OmegaPack pack;
-            for (int i = 0; i < RTDD_MAX_T; i++) pack.w[i] = (i < n) ? om[k + i] : 0.0f;
+            for (int i = 0; i < RTDD_MAX_T; i++) pack.w[i] = (i < m) ? om[k + i] : 0.0f;
             const int src = cur, dst = cur ^ 2;
-            e = rtdd::launch_sweep_blocked(cs, L, ctx->dLut, L.x[src], L.x[src + 1], L.x[dst], L.x[dst + 1], pack, T, n, gamma,
-                                           k == 0, ctx->smCount);
-            kernels++;
+            e = rtdd::launch_sweep_blocked(s, L, ctx->dLut, L.x[src], L.x[src + 1], L.x[dst], L.x[dst + 1], pack, T, m, gamma,
+                                           k == 0, ctx->smCount, (k + m >= iters) ? target : nullptr);
+            n++;
             cur = dst;
         }
         result = cur;
     }
-    cudaError_t e2 = cudaStreamEndCapture(cs, &graph);
-    if (e != cudaSuccess) { if (graph) cudaGraphDestroy(graph); return rtdd_check(ctx, e, "sweep capture"); }
-    RTDD_TRY(e2, "cudaStreamEndCapture");
-    cudaGraphExec_t exec = nullptr;
-    e = cudaGraphInstantiate(&exec, graph, 0);
-    cudaGraphDestroy(graph);
-    RTDD_TRY(e, "cudaGraphInstantiate");
-    g.exec = exec;
-    g.kernels = kernels;
-    g.resultPlane = result;
-    auto ins = ctx->graphs.emplace(key, g);
-    *out = &ins.first->second;
+    *kernels = n;
+    *resultPlane = result;
+    return rtdd_check(ctx, e, "sweep launch");
+}
+
+struct LevelArgs {
+    int level, iters;
+    float *depth; size_t depthPitch;
+    const uint8_t *scribble; size_t scribblePitch;
+    const uint8_t *gray; size_t grayPitch;
+    uint8_t *u8; size_t u8Pitch;          // optional quantised output (whole-frame path, level 0)
+};
+
+// One level on stream `s`: edge-weight pass, sweeps, result into the caller's depth plane.  `capturing` selects
+// the event-record flavour that is legal inside a stream capture.
+int enqueue_level(rtdd_ctx *ctx, cudaStream_t s, const LevelArgs &a, bool capturing, int *kernels)
+{
+    RtddLevel &L = ctx->lv[a.level];
+    const bool coarsest = (a.level == ctx->levels - 1);
+    const int threshold = (a.level == 0) ? 0 : 4;          // ref: src/GPUSolver.cu:201-202
+    int n = 0;
+    RTDD_TRY(rtdd::launch_level_init(s, L, a.depth, a.depthPitch, a.scribble, a.scribblePitch, a.gray, a.grayPitch, coarsest, threshold, L.x[0]),
+             "level init");
+    n++;
+    int plane = 0;
+    bool direct = false;
+    if (a.iters > 0) {
+        rtdd::SweepTarget tgt = {a.depth, (int)(a.depthPitch / sizeof(float)), a.u8, (int)a.u8Pitch};
+        direct = target_ok(a.depth, a.depthPitch);
+        const unsigned int flags = capturing ? cudaEventRecordExternal : cudaEventRecordDefault;
+        RTDD_TRY(cudaEventRecordWithFlags(L.evBegin, s, flags), "level event");
+        int k = 0;
+        int rc = enqueue_sweeps(ctx, s, a.level, a.iters, direct ? &tgt : nullptr, &k, &plane);
+        if (rc) return rc;
+        RTDD_TRY(cudaEventRecordWithFlags(L.evEnd, s, flags), "level event");
+        L.timed = true; L.lastIters = a.iters; L.lastKernels = k;
+        n += k;
+    }
+    if (!direct) {
+        RTDD_TRY(rtdd::launch_copy_out(s, L, L.x[plane], a.depth, a.depthPitch), "copy out");
+        n++;
+        if (a.u8) {
+            RTDD_TRY(rtdd::launch_quantise(s, a.depth, a.depthPitch, a.u8, a.u8Pitch, L.rows, L.cols), "quantise");
+            n++;
+        }
+    }
+    *kernels = n;
+    return 0;
+}
+
+// Capture `body` into a graph (or fetch it from the cache) and launch it on the context stream.
+template <class Body>
+int run_cached_graph(rtdd_ctx *ctx, const RtddGraphKey &key, Body body)
+{
+    auto it = ctx->graphs.find(key);
+    if (it == ctx->graphs.end()) {
+        if (ctx->graphs.size() >= 64) {                      // callers that keep changing planes: start over
+            RTDD_TRY(cudaStreamSynchronize(ctx->stream), "graph cache");
+            destroy_graphs(ctx);
+        }
+        cudaStream_t cs = ctx->captureStream;
+        RTDD_TRY(cudaStreamBeginCapture(cs, cudaStreamCaptureModeRelaxed), "cudaStreamBeginCapture");
+        int kernels = 0;
+        const int rc = body(cs, &kernels);
+        cudaGraph_t graph = nullptr;
+        const cudaError_t e2 = cudaStreamEndCapture(cs, &graph);
+        if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+        RTDD_TRY(e2, "cudaStreamEndCapture");
+        RtddGraph g;
+        const cudaError_t e = cudaGraphInstantiate(&g.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        RTDD_TRY(e, "cudaGraphInstantiate");
+        g.kernels = kernels;
+        it = ctx->graphs.emplace(key, g).first;
+    }
+    RTDD_TRY(cudaGraphLaunch(it->second.exec, ctx->stream), "cudaGraphLaunch");
+    ctx->launches += it->second.kernels;
     return 0;
 }
 
@@ -353,26 +419,21 @@ int rtdd_solve_level(rtdd_ctx *ctx, float *depth, size_t depthPitch, const uint8
 {
     if (!ctx) return RTDD_E_ARG;
     if (!ctx->lutLoaded) return rtdd_fail(ctx, RTDD_E_STATE, "rtdd_solve_level (rtdd_load_weights not called)");
-    if (!scribble || maxIterations < 0) return rtdd_fail(ctx, RTDD_E_ARG, "rtdd_solve_level");
-    DeviceGuard guard(ctx->device);
-    int rc = edge_pass(ctx, depth, depthPitch, scribble, scribblePitch, gray, grayPitch, rows, cols, level, "rtdd_solve_level");
-    if (rc) return rc;
+    if (!depth || !gray || !scribble || maxIterations < 0 || !level_dims_ok(ctx, level, rows, cols))
+        return rtdd_fail(ctx, RTDD_E_ARG, "rtdd_solve_level");
     RtddLevel &L = ctx->lv[level];
-    int plane = 0;
-    if (maxIterations > 0) {
-        RtddGraph *g = nullptr;
-        rc = get_sweep_graph(ctx, level, maxIterations, &g);
-        if (rc) return rc;
-        RTDD_TRY(cudaEventRecord(L.evBegin, ctx->stream), "rtdd_solve_level (event)");
-        RTDD_TRY(cudaGraphLaunch(g->exec, ctx->stream), "rtdd_solve_level (graph launch)");
-        RTDD_TRY(cudaEventRecord(L.evEnd, ctx->stream), "rtdd_solve_level (event)");
-        L.timed = true; L.lastIters = maxIterations; L.lastKernels = g->kernels;
-        ctx->launches += g->kernels;
-        plane = g->resultPlane;
-    }
-    RTDD_TRY(rtdd::launch_copy_out(ctx->stream, L, L.x[plane], depth, depthPitch), "rtdd_solve_level (copy out)");
-    ctx->launches++;
-    return 0;
+    if (rows != L.rows || cols != L.cols) return rtdd_fail(ctx, RTDD_E_ARG, "rtdd_solve_level");   // planes are sized per level (ref :42-48)
+    DeviceGuard guard(ctx->device);
+    int rc = ensure_omega_table(ctx, maxIterations);
+    if (rc) return rc;
+    int variant, T;
+    pick_variant(ctx, L, maxIterations, &variant, &T);
+    RtddGraphKey key{};
+    key.kind = 1; key.level = level; key.iters = maxIterations; key.variant = variant; key.T = T;
+    key.p[0] = depth; key.p[1] = scribble; key.p[2] = gray;
+    key.pitch[0] = depthPitch; key.pitch[1] = scribblePitch; key.pitch[2] = grayPitch;
+    const LevelArgs args{level, maxIterations, depth, depthPitch, scribble, scribblePitch, gray, grayPitch, nullptr, 0};
+    return run_cached_graph(ctx, key, [&](cudaStream_t cs, int *kernels) { return enqueue_level(ctx, cs, args, true, kernels); });
 }
 
 int rtdd_selftest_division(rtdd_ctx *ctx, unsigned long long n, unsigned long long seed, int mode, unsigned long long *mismatches)
@@ -746,34 +807,47 @@ int rtdd_frame_solve(rtdd_ctx *ctx, int maxIterations)
 {
     if (!ctx) return RTDD_E_ARG;
     if (!ctx->imageSet || !ctx->lutLoaded) return rtdd_fail(ctx, RTDD_E_STATE, "rtdd_frame_solve");
+    if (maxIterations < 0) return rtdd_fail(ctx, RTDD_E_ARG, "rtdd_frame_solve");
     DeviceGuard guard(ctx->device);
-    const int Lc = ctx->levels - 1;
-    int rc;
-    for (int l = 1; l < ctx->levels; l++) {                               // main.cpp:249
-        RtddFrameLevel &P = ctx->fl[l - 1], &F = ctx->fl[l];
-        rc = rtdd_pyrdown_annotation(ctx, P.scribble, P.scribblePitch, P.edited, P.editedPitch, P.rows, P.cols,
-                                     F.scribble, F.scribblePitch, F.edited, F.editedPitch, F.rows, F.cols);
-        if (rc) return rc;
-    }
-    {
-        RtddFrameLevel &F = ctx->fl[Lc];                                      // main.cpp:257
-        rc = rtdd_convert_to_float(ctx, F.edited, F.editedPitch, F.depth, F.depthPitch, F.scribble, F.scribblePitch, F.rows, F.cols);
-        if (rc) return rc;
-    }
-    for (int l = Lc; l >= 0; l--) {                                           // main.cpp:261-288
-        RtddFrameLevel &F = ctx->fl[l];
-        const int iters = rtdd_level_iterations(maxIterations, ctx->levels, l);
-        rc = rtdd_solve_level(ctx, F.depth, F.depthPitch, F.scribble, F.scribblePitch, F.gray, F.grayPitch, F.rows, F.cols, iters, l);
-        if (rc) return rc;
-        if (l > 0) {
-            RtddFrameLevel &N = ctx->fl[l - 1];
-            rc = rtdd_pyrup_depth(ctx, F.depth, F.depthPitch, F.rows, F.cols, N.depth, N.depthPitch, N.rows, N.cols);
-            if (rc) return rc;
-            rc = rtdd_convert_to_float(ctx, N.edited, N.editedPitch, N.depth, N.depthPitch, N.scribble, N.scribblePitch, N.rows, N.cols);
-            if (rc) return rc;
+    int rc = ensure_omega_table(ctx, maxIterations);
+    if (rc) return rc;
+    // the whole frame is ONE graph launch: every plane it touches is owned by the context, so the graph never goes stale
+    RtddGraphKey key{};
+    key.kind = 2; key.iters = maxIterations; key.variant = ctx->variant; key.T = ctx->sweepsPerPass;
+    return run_cached_graph(ctx, key, [&](cudaStream_t cs, int *kernels) -> int {
+        const int Lc = ctx->levels - 1;
+        int n = 0;
+        for (int l = 1; l < ctx->levels; l++) {                               // main.cpp:249
+            RtddFrameLevel &P = ctx->fl[l - 1], &F = ctx->fl[l];
+            RTDD_TRY(rtdd::launch_pyrdown_annotation(cs, P.scribble, P.scribblePitch, P.edited, P.editedPitch, P.rows, P.cols,
+                                                     F.scribble, F.scribblePitch, F.edited, F.editedPitch, F.rows, F.cols), "frame: annotation");
+            n++;
         }
-    }
-    return rtdd_quantise_u8(ctx, ctx->fl[0].depth, ctx->fl[0].depthPitch, ctx->depthU8, ctx->depthU8Pitch, ctx->rows, ctx->cols);  // main.cpp:290
+        {
+            RtddFrameLevel &F = ctx->fl[Lc];                                      // main.cpp:257
+            RTDD_TRY(rtdd::launch_convert(cs, F.edited, F.editedPitch, F.depth, F.depthPitch, F.scribble, F.scribblePitch, F.rows, F.cols), "frame: convert");
+            n++;
+        }
+        for (int l = Lc; l >= 0; l--) {                                           // main.cpp:261-288
+            RtddFrameLevel &F = ctx->fl[l];
+            const int iters = rtdd_level_iterations(maxIterations, ctx->levels, l);
+            // level 0 also emits the 8-bit map (main.cpp:290) from its last sweep pass
+            const LevelArgs args{l, iters, F.depth, F.depthPitch, F.scribble, F.scribblePitch, F.gray, F.grayPitch,
+                                 l == 0 ? ctx->depthU8 : nullptr, l == 0 ? ctx->depthU8Pitch : 0};
+            int k = 0;
+            const int r = enqueue_level(ctx, cs, args, true, &k);
+            if (r) return r;
+            n += k;
+            if (l > 0) {
+                RtddFrameLevel &N = ctx->fl[l - 1];
+                RTDD_TRY(rtdd::launch_pyrup_depth(cs, F.depth, F.depthPitch, F.rows, F.cols, N.depth, N.depthPitch, N.rows, N.cols), "frame: pyrUp");
+                RTDD_TRY(rtdd::launch_convert(cs, N.edited, N.editedPitch, N.depth, N.depthPitch, N.scribble, N.scribblePitch, N.rows, N.cols), "frame: convert");
+                n += 2;
+            }
+        }
+        *kernels = n;
+        return 0;
+    });
 }
 
 int rtdd_frame_solve_host(rtdd_ctx *ctx, const uint8_t *scribbleHost, size_t scribblePitch,

@@ -6,6 +6,7 @@
 #include <stddef.h>
 
 #include <map>
+#include <tuple>
 #include <string>
 #include <vector>
 
@@ -41,12 +42,14 @@ struct RtddFrameLevel {
 };
 
 struct RtddGraphKey {
+    int kind;            // 1 = one level (rtdd_solve_level), 2 = whole frame (rtdd_frame_solve)
     int level, iters, variant, T;
-    bool operator<(const RtddGraphKey &o) const {
-        if (level != o.level) return level < o.level;
-        if (iters != o.iters) return iters < o.iters;
-        if (variant != o.variant) return variant < o.variant;
-        return T < o.T;
+    const void *p[3];    // caller planes baked into the graph: depth, scribble, gray
+    size_t pitch[3];
+    bool operator<(const RtddGraphKey &o) const
+    {
+        return std::tie(kind, level, iters, variant, T, p[0], p[1], p[2], pitch[0], pitch[1], pitch[2]) <
+               std::tie(o.kind, o.level, o.iters, o.variant, o.T, o.p[0], o.p[1], o.p[2], o.pitch[0], o.pitch[1], o.pitch[2]);
     }
 };
 
@@ -96,22 +99,29 @@ static inline size_t rtdd_round_up(size_t a, size_t b) { return (a + b - 1) / b 
 namespace rtdd {
 
 // solver_kernels.cu
+// A caller-visible destination for the LAST sweep pass of a level: the pitched depth plane (16-byte aligned rows)
+// and optionally the 8-bit quantised map.  Null = the library's own planes.
+struct SweepTarget {
+    float *x; int pitchX;        // floats per row
+    uint8_t *u8; int pitchU8;    // may be null
+};
 cudaError_t launch_level_init(cudaStream_t s, const RtddLevel &L, const float *depth, size_t depthPitch,
                               const uint8_t *scribble, size_t scribblePitch,
                               const uint8_t *gray, size_t grayPitch, bool coarsest, int threshold, float *x0);
 cudaError_t launch_sweep_single(cudaStream_t s, const RtddLevel &L, const float *lut, const float *x, const float *prev,
-                                float *out, float omega, float gamma, bool firstSweep);
+                                float *out, float omega, float gamma, bool firstSweep, const SweepTarget *target = nullptr);
 // temporally blocked: T sweeps (x, prev) -> (xOut, prevOut); omegas passed by value (<= RTDD_MAX_T)
 #define RTDD_MAX_T 16
 struct OmegaPack { float w[RTDD_MAX_T]; };
 cudaError_t launch_sweep_blocked(cudaStream_t s, const RtddLevel &L, const float *lut, const float *x, const float *prev,
-                                 float *xOut, float *prevOut, OmegaPack om, int T, int nsweeps, float gamma, bool firstSweep, int smCount);
+                                 float *xOut, float *prevOut, OmegaPack om, int T, int nsweeps, float gamma, bool firstSweep, int smCount,
+                                 const SweepTarget *target = nullptr);
 int blocked_max_T();
 void set_blocked_tile_override(int tile);
 // resident (one cluster, all sweeps in one launch); omegas = device array of nsweeps floats
 bool resident_plan(int rows, int cols, int *R, int *clusterSize, int *blocksPerCta, int *WX);
 cudaError_t launch_sweep_resident(cudaStream_t s, const RtddLevel &L, const float *lut, const float *x, float *xOut,
-                                  const float *omegas, int nsweeps, float gamma);
+                                  const float *omegas, int nsweeps, float gamma, const SweepTarget *target = nullptr);
 cudaError_t launch_division_selftest(cudaStream_t s, unsigned long long n, unsigned long long seed, int mode, unsigned long long *dMismatches);
 cudaError_t launch_copy_out(cudaStream_t s, const RtddLevel &L, const float *x, float *depth, size_t depthPitch);
 cudaError_t launch_export_links(cudaStream_t s, const RtddLevel &L, uint8_t *linkRight, uint8_t *linkDown, size_t outPitch);

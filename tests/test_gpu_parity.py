@@ -165,7 +165,7 @@ def test_call_order_and_argument_errors(rtdd):
         ctx.matrix_free_solver(d[:32], s[:32], g[:32], 3, 0)   # size does not match the level's planes
     ctx.matrix_free_solver(d, s, g, 3, 0)
     ctx.sync()
-    assert ctx.launch_count >= 3
+    assert ctx.launch_count >= 2
     ctx.close()
 
 
