@@ -61,6 +61,42 @@ void omega_schedule(int iterations, std::vector<float> &om)
     }
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+bool encode_plane_map(EncodeTiledFn fn, CUtensorMap *map, void *base, bool f32, int widthElems, int rows, int boxW, int boxH)
+{
+    const cuuint64_t dims[2] = {(cuuint64_t)widthElems, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)widthElems * (f32 ? 4u : 1u)};
+    const cuuint32_t box[2] = {(cuuint32_t)boxW, (cuuint32_t)boxH};
+    const cuuint32_t estr[2] = {1, 1};
+    return fn(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+void build_tensor_maps(rtdd_ctx *ctx)
+{
+    void *fnp = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fnp, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !fnp) {
+        cudaGetLastError();
+        return;                          // levels keep hasMaps = false: the LDG form of the blocked kernel is used
+    }
+    EncodeTiledFn fn = (EncodeTiledFn)fnp;
+    for (auto &L : ctx->lv) {
+        bool ok = true;
+        for (int k = 0; k < 4 && ok; k++) ok = encode_plane_map(fn, &L.tmX[k], L.x[k], true, L.pitchF, L.rows, 128, 64);
+        // byte boxes are 144 wide: see TmaSmem::WB in solver_kernels.cu
+        ok = ok && encode_plane_map(fn, &L.tmLinkR, L.linkR, false, L.pitchB, L.rows, 144, 64);
+        ok = ok && encode_plane_map(fn, &L.tmLinkD, L.linkD, false, L.pitchB, L.rows, 144, 64);
+        ok = ok && encode_plane_map(fn, &L.tmMask, L.mask, false, L.pitchB, L.rows, 144, 64);
+        L.hasMaps = ok;
+    }
+}
+
 void destroy_graphs(rtdd_ctx *ctx)
 {
     for (auto &kv : ctx->graphs)
@@ -313,6 +349,7 @@ int rtdd_create(int rows, int cols, int levels, int device, rtdd_ctx **out)
         L.linkD = (uint8_t *)p; p += rtdd_round_up((size_t)L.pitchB * L.rows, 256);
         L.mask = (uint8_t *)p;  p += rtdd_round_up((size_t)L.pitchB * L.rows, 256);
     }
+    build_tensor_maps(ctx);
     for (int l = 0; l < levels && e == cudaSuccess; l++) {
         e = cudaEventCreate(&ctx->lv[l].evBegin);
         if (e == cudaSuccess) e = cudaEventCreate(&ctx->lv[l].evEnd);
@@ -381,6 +418,13 @@ int rtdd_set_tuning(rtdd_ctx *ctx, const char *key, int value)
     if (!ctx || !key) return RTDD_E_ARG;
     if (strcmp(key, "blocked_tile") == 0 && (value == 0 || value == 32 || value == 64)) {
         rtdd::set_blocked_tile_override(value);
+        DeviceGuard guard(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+        destroy_graphs(ctx);
+        return 0;
+    }
+    if (strcmp(key, "blocked_tma") == 0 && (value == 0 || value == 1)) {
+        rtdd::set_blocked_tma(value);
         DeviceGuard guard(ctx->device);
         cudaStreamSynchronize(ctx->stream);
         destroy_graphs(ctx);

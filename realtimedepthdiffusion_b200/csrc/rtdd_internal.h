@@ -1,6 +1,7 @@
 // Internal declarations shared by the translation units of librtdd.so.
 #pragma once
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stddef.h>
@@ -23,6 +24,9 @@ struct RtddLevel {
     uint8_t *linkR = nullptr;  // LUT index of link (x,y)-(x+1,y)
     uint8_t *linkD = nullptr;  // LUT index of link (x,y)-(x,y+1)
     uint8_t *mask = nullptr;   // 0xFF where the scribble plane == 255 (Dirichlet), else 0
+    // TMA descriptors of the planes above (128x64-element boxes), built once in rtdd_create
+    CUtensorMap tmX[4], tmLinkR, tmLinkD, tmMask;
+    bool hasMaps = false;
     // events bracketing the most recent sweep graph of this level (rtdd_level_sweep_ms)
     cudaEvent_t evBegin = nullptr, evEnd = nullptr;
     bool timed = false;
@@ -118,6 +122,7 @@ cudaError_t launch_sweep_blocked(cudaStream_t s, const RtddLevel &L, const float
                                  const SweepTarget *target = nullptr);
 int blocked_max_T();
 void set_blocked_tile_override(int tile);
+void set_blocked_tma(int enabled);
 // resident (one cluster, all sweeps in one launch); omegas = device array of nsweeps floats
 bool resident_plan(int rows, int cols, int *R, int *clusterSize, int *blocksPerCta, int *WX);
 cudaError_t launch_sweep_resident(cudaStream_t s, const RtddLevel &L, const float *lut, const float *x, float *xOut,
