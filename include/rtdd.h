@@ -106,7 +106,7 @@ int rtdd_selftest_division(rtdd_ctx *ctx, unsigned long long n, unsigned long lo
  * bit-identical by construction; the selector exists for tests and profiling. */
 int rtdd_set_sweep_variant(rtdd_ctx *ctx, int variant, int sweepsPerPass);
 /* Process-wide tuning knobs for experiments (tools/tune_blocked.py); results never change, only speed.
- * "blocked_tile": 0 auto, 64 = 128x64-pixel regions, 32 = 128x32-pixel regions;
+ * "blocked_tile": 0 auto, 64 = 128x64-pixel regions, 34 = 128x32 regions with 2 rows per warp, 32 = 128x32 with 4 rows per warp;
  * "blocked_tma": 1 (default) TMA-fed persistent form of the 128x64 kernel, 0 = plain LDG form. */
 int rtdd_set_tuning(rtdd_ctx *ctx, const char *key, int value);
 

@@ -416,7 +416,7 @@ int rtdd_levels(const rtdd_ctx *ctx) { return ctx ? ctx->levels : 0; }
 int rtdd_set_tuning(rtdd_ctx *ctx, const char *key, int value)
 {
     if (!ctx || !key) return RTDD_E_ARG;
-    if (strcmp(key, "blocked_tile") == 0 && (value == 0 || value == 32 || value == 64)) {
+    if (strcmp(key, "blocked_tile") == 0 && (value == 0 || value == 32 || value == 34 || value == 64)) {
         rtdd::set_blocked_tile_override(value);
         DeviceGuard guard(ctx->device);
         cudaStreamSynchronize(ctx->stream);

@@ -62,7 +62,7 @@ def test_solve_level_bit_exact_vs_oracle(rtdd, rows, cols, variant, T):
             "level %d: max |diff| %g on %d px" % (level, np.abs(got - want).max(), (got != want).sum())
 
 
-@pytest.mark.parametrize("tile,tma", [(64, 1), (64, 0), (32, 0)])
+@pytest.mark.parametrize("tile,tma", [(64, 1), (64, 0), (32, 0), (34, 0)])
 @pytest.mark.parametrize("rows,cols", [(1, 1), (64, 128), (65, 129), (67, 120), (203, 317), (270, 480), (300, 700)])
 def test_blocked_kernel_forms_agree(rtdd, rows, cols, tile, tma):
     """128x64 regions through TMA (persistent) and through LDG, and 128x32 regions: all bit-identical to the oracle."""

@@ -16,9 +16,9 @@ rows, cols, seed = WORKLOADS[name]
 bgr, scribble, edited = synth.synth_case(rows, cols, seed)
 out = np.zeros((rows, cols), np.uint8)
 table = {}
-for tile in (64, 32):
+for tile in (64, 32, 34):
     for T in (4, 5, 6, 7, 8, 9, 10, 11, 12, 14, 16):
-        if tile == 32 and 2 * T >= 32:
+        if tile in (32, 34) and 2 * T >= 32:
             continue
         ctx = rtdd.DepthDiffusion(rows, cols)
         ctx.set_tuning("blocked_tile", tile)
