@@ -167,7 +167,7 @@ def run_native(args, dist, rank, world, local):
     from realtimedepthdiffusion_b200 import synth
     rows, cols, seed = WORKLOADS[args.workload]
     # configs[3]: image i -> rank i mod N; every rank gets its own seed
-    bgr, scribble, edited = synth.synth_case(rows, cols, seed + rank)
+    bgr, scribble, edited = synth.synth_case(rows, cols, seed + rank + args.seed_offset)
     ctx = rtdd.DepthDiffusion(rows, cols)
     stream = torch.cuda.Stream()
     ctx.set_stream(stream)
@@ -400,6 +400,7 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default="4k", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--seed-offset", type=int, default=0, help="extra offset on the synthetic image seed (diagnostics)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if not torch.cuda.is_available():

@@ -97,7 +97,8 @@ int rtdd_level_sweep_ms(rtdd_ctx *ctx, int level, float *ms, int *iterations, in
 /* Self-test of the sweep kernels' branch-free division (csrc/solver_kernels.cu: div_fast) against the
  * compiler's IEEE div.rn (the operation the reference's `sum / count` compiles to, ref: src/GPUSolver.cu:104)
  * on n counter-generated operand pairs.  mode 0 = the whole admitted range, 1 = the sweep's typical range,
- * 2 = quotients placed next to rounding boundaries.  *mismatches (HOST) must come back 0. */
+ * 2 = quotients placed next to rounding boundaries, 3 = tiny/denormal denominators through the exact power-of-two
+ * rescaling the resident kernel uses.  *mismatches (HOST) must come back 0. */
 int rtdd_selftest_division(rtdd_ctx *ctx, unsigned long long n, unsigned long long seed, int mode, unsigned long long *mismatches);
 
 /* Sweep implementation selector for rtdd_solve_level: 0 = auto (default),

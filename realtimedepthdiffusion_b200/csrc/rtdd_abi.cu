@@ -483,7 +483,7 @@ int rtdd_solve_level(rtdd_ctx *ctx, float *depth, size_t depthPitch, const uint8
 int rtdd_selftest_division(rtdd_ctx *ctx, unsigned long long n, unsigned long long seed, int mode, unsigned long long *mismatches)
 {
     if (!ctx) return RTDD_E_ARG;
-    if (!mismatches || mode < 0 || mode > 2) return rtdd_fail(ctx, RTDD_E_ARG, "rtdd_selftest_division");
+    if (!mismatches || mode < 0 || mode > 3) return rtdd_fail(ctx, RTDD_E_ARG, "rtdd_selftest_division");
     DeviceGuard guard(ctx->device);
     unsigned long long *d = nullptr;
     RTDD_TRY(cudaMalloc((void **)&d, sizeof(*d)), "rtdd_selftest_division");

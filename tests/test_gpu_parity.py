@@ -152,7 +152,7 @@ def test_edge_weight_pass_vs_oracle(rtdd, rows, cols, level, levels):
 
 def test_branch_free_division_matches_ieee_division(rtdd):
     ctx = rtdd.DepthDiffusion(8, 8, 1)
-    for mode in (0, 1, 2):
+    for mode in (0, 1, 2, 3):
         assert ctx.selftest_division(1 << 31, seed=12345 + mode, mode=mode) == 0, mode
     ctx.close()
 
@@ -175,6 +175,29 @@ def test_slow_path_inputs_denormal_and_huge_depths(rtdd):
             ctx.sync()
             assert np.array_equal(to_host(d).view(np.uint32), want.view(np.uint32)), (level, variant)
             ctx.close()
+
+
+@pytest.mark.parametrize("rows,cols,level,levels", [(67, 120, 0, 1), (135, 240, 1, 2), (300, 520, 0, 1), (300, 520, 1, 2)])
+def test_salt_and_pepper_image_tiny_weight_sums(rtdd, rows, cols, level, levels):
+    """Isolated pixels whose four neighbours are all across 200+ grey-level edges: weight sums down to fp32 denormals.
+    The resident kernel rescales them exactly, the blocked kernels fall back per thread; all bit-identical to the oracle."""
+    rng = np.random.default_rng(rows + level)
+    gray = np.full((rows, cols), 128, np.uint8)
+    gray[rng.random((rows, cols)) < 0.03] = 255
+    gray[rng.random((rows, cols)) < 0.03] = 0
+    gray[10:14, 10:14] = np.array([[0, 255, 0, 255], [255, 0, 255, 0], [0, 255, 0, 255], [255, 0, 255, 0]], np.uint8)   # checkerboard
+    depth = rng.uniform(0, 255, (rows, cols)).astype(np.float32)
+    depth[20:30, 20:60] = 0.0
+    scribble = np.where(rng.random((rows, cols)) < 0.05, 255, 0).astype(np.uint8)
+    want = ob.solve_level(depth, scribble, gray, 40, level, levels - 1)
+    for variant, T in ((1, 0), (2, 8), (3, 0), (0, 0)):
+        ctx = rtdd.DepthDiffusion(rows << level, cols << level, levels)
+        ctx.set_sweep_variant(variant, T)
+        d, s, g = to_dev(depth), to_dev(scribble), to_dev(gray)
+        ctx.matrix_free_solver(d, s, g, 40, level)
+        ctx.sync()
+        assert np.array_equal(to_host(d).view(np.uint32), want.view(np.uint32)), (variant, T)
+        ctx.close()
 
 
 def test_call_order_and_argument_errors(rtdd):
