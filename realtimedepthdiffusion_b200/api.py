@@ -133,6 +133,12 @@ class DepthDiffusion:
         self._ck(lib.rtdd_selftest_division(self._h, int(n), int(seed), int(mode), C.byref(mism)))
         return mism.value
 
+    def edge_weights_only(self, depth, gray, level):
+        """The edge-weight pass without exporting the link planes (timing)."""
+        rows, cols = depth.shape
+        self._ck(lib.rtdd_edge_weights(self._h, _ptr(depth), _pitch(depth), _ptr(gray), _pitch(gray), rows, cols, int(level),
+                                       C.c_void_p(0), C.c_void_p(0), 0))
+
     def edge_weights(self, depth, gray, level):
         rows, cols = depth.shape
         right = pitched_empty(rows, cols, torch.uint8, self.device)

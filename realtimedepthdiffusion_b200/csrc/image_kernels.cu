@@ -25,9 +25,37 @@ convert_kernel(const uint8_t *__restrict__ src, size_t srcPitch, float *__restri
     }
 }
 
+// 4 pixels per thread: one 32-bit mask word decides; untouched groups (the common case) cost 1 byte per pixel
+__global__ void __launch_bounds__(256)
+convert4_kernel(const uint8_t *__restrict__ src, size_t srcPitch, float *__restrict__ dst, size_t dstPitch,
+                const uint8_t *__restrict__ mask, size_t maskPitch, int rows, int cols)
+{
+    const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x4 >= cols || y >= rows) return;
+    float *dRow = (float *)((char *)dst + (size_t)y * dstPitch) + x4;
+    const uint8_t *sRow = src + (size_t)y * srcPitch + 3 * x4;
+    if (x4 + 4 <= cols) {
+        const unsigned int m = __ldg((const unsigned int *)(mask + (size_t)y * maskPitch + x4));
+        if (!((m & 0xFFu) == 0xFFu || ((m >> 8) & 0xFFu) == 0xFFu || ((m >> 16) & 0xFFu) == 0xFFu || (m >> 24) == 0xFFu)) return;
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            if (((m >> (8 * i)) & 0xFFu) == 0xFFu) dRow[i] = (float)__ldg(sRow + 3 * i);
+    } else {
+        for (int i = 0; x4 + i < cols; i++)
+            if (__ldg(mask + (size_t)y * maskPitch + x4 + i) == 255) dRow[i] = (float)__ldg(sRow + 3 * i);
+    }
+}
+
 cudaError_t launch_convert(cudaStream_t s, const uint8_t *src, size_t srcPitch, float *dst, size_t dstPitch,
                            const uint8_t *mask, size_t maskPitch, int rows, int cols)
 {
+    if ((((uintptr_t)mask | maskPitch) & 3u) == 0) {
+        dim3 block(64, 4);
+        dim3 grid(rtdd_div_up(rtdd_div_up(cols, 4), block.x), rtdd_div_up(rows, block.y));
+        convert4_kernel<<<grid, block, 0, s>>>(src, srcPitch, dst, dstPitch, mask, maskPitch, rows, cols);
+        return cudaGetLastError();
+    }
     dim3 block(64, 4);
     dim3 grid(rtdd_div_up(cols, block.x), rtdd_div_up(rows, block.y));
     convert_kernel<<<grid, block, 0, s>>>(src, srcPitch, dst, dstPitch, mask, maskPitch, rows, cols);
@@ -68,11 +96,85 @@ pyrdown_annotation_kernel(const uint8_t *__restrict__ prevScribble, size_t prevS
     }
 }
 
+// 4 output pixels per thread: the 2 x 9 mask bytes they look at are fetched as two 64-bit words (+1 byte each);
+// groups without any scribble (the common case) leave after that
+__global__ void __launch_bounds__(256)
+pyrdown_annotation4_kernel(const uint8_t *__restrict__ prevScribble, size_t prevScribblePitch,
+                           const uint8_t *__restrict__ prevEdited, size_t prevEditedPitch, int previousRows, int previousCols,
+                           uint8_t *__restrict__ currScribble, size_t currScribblePitch,
+                           uint8_t *__restrict__ currEdited, size_t currEditedPitch, int currentRows, int currentCols)
+{
+    const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x4 >= currentCols || y >= currentRows) return;
+    const int px0 = 2 * x4;                       // window columns px0-1 .. px0+6
+    const bool fast = (px0 + 8 <= previousCols) && (x4 + 4 <= currentCols);
+    if (fast) {
+        unsigned long long w[2] = {0ull, 0ull};
+        unsigned int before[2] = {0u, 0u};
+        bool any = false;
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            const int py = 2 * y - 1 + j;
+            if (py < 0 || py >= previousRows) continue;
+            const uint8_t *row = prevScribble + (size_t)py * prevScribblePitch;
+            w[j] = __ldg((const unsigned long long *)(row + px0));
+            if (px0 > 0) before[j] = __ldg(row + px0 - 1);
+            // any byte equal to 0xFF?  (classic has-zero-byte test on the complement)
+            const unsigned long long v = ~w[j];
+            any = any || (((v - 0x0101010101010101ull) & ~v & 0x8080808080808080ull) != 0ull) || before[j] == 255u;
+        }
+        if (!any) return;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            int hitX = -1, hitY = -1;
+#pragma unroll
+            for (int dy = 0; dy >= -1; dy--) {
+#pragma unroll
+                for (int dx = 0; dx >= -1; dx--) {
+                    const int c = 2 * i + dx;             // column relative to px0
+                    const int j = dy + 1;
+                    const unsigned int b = (c < 0) ? before[j] : (unsigned int)((w[j] >> (8 * c)) & 0xFFull);
+                    const int py = 2 * y + dy, px = px0 + c;
+                    if (hitX < 0 && px >= 0 && py >= 0 && py < previousRows && b == 255u) { hitX = px; hitY = py; }
+                }
+            }
+            if (hitX >= 0) {
+                currScribble[(size_t)y * currScribblePitch + x4 + i] = 255;
+                currEdited[(size_t)y * currEditedPitch + 3 * (x4 + i)] = __ldg(prevEdited + (size_t)hitY * prevEditedPitch + 3 * hitX);
+            }
+        }
+        return;
+    }
+    for (int i = 0; i < 4 && x4 + i < currentCols; i++) {
+        const int x = x4 + i;
+        int hitX = -1, hitY = -1;
+        for (int dy = 0; dy >= -1; dy--)
+            for (int dx = 0; dx >= -1; dx--) {
+                const int px = 2 * x + dx, py = 2 * y + dy;
+                if (hitX < 0 && px >= 0 && py >= 0 && px < previousCols && py < previousRows &&
+                    __ldg(prevScribble + (size_t)py * prevScribblePitch + px) == 255) { hitX = px; hitY = py; }
+            }
+        if (hitX >= 0) {
+            currScribble[(size_t)y * currScribblePitch + x] = 255;
+            currEdited[(size_t)y * currEditedPitch + 3 * x] = __ldg(prevEdited + (size_t)hitY * prevEditedPitch + 3 * hitX);
+        }
+    }
+}
+
 cudaError_t launch_pyrdown_annotation(cudaStream_t s, const uint8_t *prevScribble, size_t prevScribblePitch,
                                       const uint8_t *prevEdited, size_t prevEditedPitch, int previousRows, int previousCols,
                                       uint8_t *currScribble, size_t currScribblePitch, uint8_t *currEdited, size_t currEditedPitch,
                                       int currentRows, int currentCols)
 {
+    if ((((uintptr_t)prevScribble | prevScribblePitch) & 7u) == 0) {
+        dim3 block(64, 4);
+        dim3 grid(rtdd_div_up(rtdd_div_up(currentCols, 4), block.x), rtdd_div_up(currentRows, block.y));
+        pyrdown_annotation4_kernel<<<grid, block, 0, s>>>(prevScribble, prevScribblePitch, prevEdited, prevEditedPitch,
+                                                          previousRows, previousCols, currScribble, currScribblePitch,
+                                                          currEdited, currEditedPitch, currentRows, currentCols);
+        return cudaGetLastError();
+    }
     dim3 block(64, 4);
     dim3 grid(rtdd_div_up(currentCols, block.x), rtdd_div_up(currentRows, block.y));
     pyrdown_annotation_kernel<<<grid, block, 0, s>>>(prevScribble, prevScribblePitch, prevEdited, prevEditedPitch,
@@ -229,6 +331,70 @@ pyrup_depth_kernel(const float *__restrict__ src, size_t srcPitch, int srows, in
     }
 }
 
+// Interior fast path: one thread produces destination columns 4j..4j+3 of the row pair (2y, 2y+1) from source
+// columns 2j-1..2j+2 of source rows y-1, y, y+1 -- the same expressions, in the same order, as pyrup_h and the scalar
+// kernel (bit-identical); border columns / rows and odd-sized destinations go through the scalar expressions.
+__device__ __forceinline__ void pyrup_h4(const float *__restrict__ s, int j, float (&r)[4])
+{
+    const float a = __ldg(s + 2 * j - 1), b = __ldg(s + 2 * j), c = __ldg(s + 2 * j + 1), d = __ldg(s + 2 * j + 2);
+    r[0] = __fadd_rn(__fadd_rn(a, __fmul_rn(b, 6.0f)), c);
+    r[1] = __fmul_rn(__fadd_rn(b, c), 4.0f);
+    r[2] = __fadd_rn(__fadd_rn(b, __fmul_rn(c, 6.0f)), d);
+    r[3] = __fmul_rn(__fadd_rn(c, d), 4.0f);
+}
+
+__global__ void __launch_bounds__(256)
+pyrup_depth4_kernel(const float *__restrict__ src, size_t srcPitch, int srows, int scols,
+                    float *__restrict__ dst, size_t dstPitch, int drows, int dcols, int rowBegin, int rowEnd)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;            // destination columns 4j..4j+3
+    const int y = (rowBegin >> 1) + blockIdx.y * blockDim.y + threadIdx.y;   // source row; destination rows 2y, 2y+1
+    const int dx0 = 4 * j;
+    if (dx0 >= dcols || 2 * y >= rowEnd || y >= srows) return;
+    const bool colFast = (2 * j - 1 >= 0) && (2 * j + 2 <= scols - 1) && (dx0 + 4 <= dcols);
+    const bool rowFast = (y >= 1) && (y + 1 <= srows - 1);
+    if (colFast && rowFast) {
+        float r0[4], r1[4], r2[4];
+        pyrup_h4((const float *)((const char *)src + (size_t)(y - 1) * srcPitch), j, r0);
+        pyrup_h4((const float *)((const char *)src + (size_t)y * srcPitch), j, r1);
+        pyrup_h4((const float *)((const char *)src + (size_t)(y + 1) * srcPitch), j, r2);
+        float e[4], o[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            e[i] = __fmul_rn(__fadd_rn(__fadd_rn(r0[i], __fmul_rn(r1[i], 6.0f)), r2[i]), 1.0f / 64.0f);
+            o[i] = __fmul_rn(__fadd_rn(r1[i], r2[i]), 1.0f / 16.0f);
+        }
+        if (2 * y >= rowBegin) *(float4 *)((float *)((char *)dst + (size_t)(2 * y) * dstPitch) + dx0) = make_float4(e[0], e[1], e[2], e[3]);
+        if (2 * y + 1 < rowEnd) *(float4 *)((float *)((char *)dst + (size_t)(2 * y + 1) * dstPitch) + dx0) = make_float4(o[0], o[1], o[2], o[3]);
+        return;
+    }
+    // borders: the scalar expressions, pixel by pixel (also the extra row / column of an odd-sized destination)
+    const int yLast = (y == srows - 1) ? drows - 1 : 2 * y + 1;    // the last source row also produces the odd extra row
+    for (int dy = 2 * y; dy <= yLast; dy++) {
+        if (dy < rowBegin || dy >= rowEnd) continue;
+        int sy2 = dy;
+        if (sy2 >= 2 * srows) sy2 = 2 * srows - 2;
+        const int sy = sy2 >> 1;
+        const int ym = (sy > 0) ? sy - 1 : (srows > 1 ? 1 : 0);
+        const int yp = (sy < srows - 1) ? sy + 1 : srows - 1;
+        const float *s0 = (const float *)((const char *)src + (size_t)ym * srcPitch);
+        const float *s1 = (const float *)((const char *)src + (size_t)sy * srcPitch);
+        const float *s2 = (const float *)((const char *)src + (size_t)yp * srcPitch);
+        const int dxEnd = (dx0 + 4 < dcols) ? dx0 + 4 : dcols;
+        for (int dx = dx0; dx < dxEnd; dx++) {
+            float *out = (float *)((char *)dst + (size_t)dy * dstPitch) + dx;
+            const float r1 = pyrup_h(s1, scols, dx);
+            const float r2 = pyrup_h(s2, scols, dx);
+            if (sy2 & 1) {
+                *out = __fmul_rn(__fadd_rn(r1, r2), 1.0f / 16.0f);
+            } else {
+                const float r0 = pyrup_h(s0, scols, dx);
+                *out = __fmul_rn(__fadd_rn(__fadd_rn(r0, __fmul_rn(r1, 6.0f)), r2), 1.0f / 64.0f);
+            }
+        }
+    }
+}
+
 cudaError_t launch_pyrup_depth(cudaStream_t s, const float *src, size_t srcPitch, int srows, int scols,
                                float *dst, size_t dstPitch, int drows, int dcols)
 {
@@ -240,6 +406,15 @@ cudaError_t launch_pyrup_depth_rows(cudaStream_t s, const float *src, size_t src
                                     float *dst, size_t dstPitch, int drows, int dcols, int rowBegin, int rowEnd)
 {
     if (rowEnd <= rowBegin) return cudaSuccess;
+    if ((((uintptr_t)dst | dstPitch) & 15u) == 0 && srows >= 2 && scols >= 2) {
+        // source rows rowBegin/2 .. (rowEnd-1)/2 (the last source row also covers an odd destination's extra row)
+        int y0 = rowBegin >> 1, y1 = (rowEnd - 1) >> 1;
+        if (y1 > srows - 1) y1 = srows - 1;
+        dim3 block(32, 8);
+        dim3 grid(rtdd_div_up(rtdd_div_up(dcols, 4), block.x), rtdd_div_up(y1 - y0 + 1, block.y));
+        pyrup_depth4_kernel<<<grid, block, 0, s>>>(src, srcPitch, srows, scols, dst, dstPitch, drows, dcols, rowBegin, rowEnd);
+        return cudaGetLastError();
+    }
     dim3 block(64, 4);
     dim3 grid(rtdd_div_up(dcols, block.x), rtdd_div_up(rowEnd - rowBegin, block.y));
     pyrup_depth_kernel<<<grid, block, 0, s>>>(src, srcPitch, srows, scols, dst, dstPitch, rowEnd, dcols, rowBegin);
@@ -261,8 +436,41 @@ quantise_kernel(const float *__restrict__ src, size_t srcPitch, uint8_t *__restr
     dst[(size_t)y * dstPitch + x] = (uint8_t)q;
 }
 
+__global__ void __launch_bounds__(256)
+quantise8_kernel(const float *__restrict__ src, size_t srcPitch, uint8_t *__restrict__ dst, size_t dstPitch, int rows, int cols)
+{
+    const int x8 = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x8 >= cols || y >= rows) return;
+    const float *sRow = (const float *)((const char *)src + (size_t)y * srcPitch) + x8;
+    uint8_t *dRow = dst + (size_t)y * dstPitch + x8;
+    if (x8 + 8 <= cols) {
+        const float4 a = __ldg((const float4 *)sRow), b = __ldg((const float4 *)sRow + 1);
+        const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        unsigned int w[2] = {0u, 0u};
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            int q = __float2int_rn(v[i]);
+            q = q < 0 ? 0 : (q > 255 ? 255 : q);
+            w[i >> 2] |= (unsigned int)q << (8 * (i & 3));
+        }
+        *(uint2 *)dRow = make_uint2(w[0], w[1]);
+    } else {
+        for (int i = 0; x8 + i < cols; i++) {
+            int q = __float2int_rn(__ldg(sRow + i));
+            dRow[i] = (uint8_t)(q < 0 ? 0 : (q > 255 ? 255 : q));
+        }
+    }
+}
+
 cudaError_t launch_quantise(cudaStream_t s, const float *src, size_t srcPitch, uint8_t *dst, size_t dstPitch, int rows, int cols)
 {
+    if ((((uintptr_t)src | srcPitch) & 15u) == 0 && (((uintptr_t)dst | dstPitch) & 7u) == 0) {
+        dim3 block(64, 4);
+        dim3 grid(rtdd_div_up(rtdd_div_up(cols, 8), block.x), rtdd_div_up(rows, block.y));
+        quantise8_kernel<<<grid, block, 0, s>>>(src, srcPitch, dst, dstPitch, rows, cols);
+        return cudaGetLastError();
+    }
     dim3 block(64, 4);
     dim3 grid(rtdd_div_up(cols, block.x), rtdd_div_up(rows, block.y));
     quantise_kernel<<<grid, block, 0, s>>>(src, srcPitch, dst, dstPitch, rows, cols);

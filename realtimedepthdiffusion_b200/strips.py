@@ -70,8 +70,11 @@ def frame_coroutine(engine, rank, nranks, max_iterations, halo=8, min_strip_pixe
     sizes = engine.sizes
     L = len(sizes)
     plan = plan_strips(sizes, nranks, halo, min_strip_pixels)
+    mark = getattr(engine, "mark", lambda label: None)           # optional per-phase device timestamps
+    mark("begin")
     engine.annotation_pyramid()                                   # main.cpp:249 (replicated: u8 planes, cheap)
     engine.convert_rows(L - 1, 0, sizes[L - 1][0])                # main.cpp:257
+    mark("annotation")
     for l in range(L - 1, -1, -1):
         iters = level_iterations(max_iterations, L, l)
         rows = sizes[l][0]
@@ -99,6 +102,7 @@ def frame_coroutine(engine, rank, nranks, max_iterations, halo=8, min_strip_pixe
                 engine.strip_finish(l, w0, w1)                    # owned rows + freshly exchanged ghosts
             else:
                 engine.strip_finish(l, a, b)                      # finest level: ghosts are stale and not needed
+        mark("solve L%d" % l)
         if l > 0:
             nrows = sizes[l - 1][0]
             if plan[l - 1] is None:
@@ -108,8 +112,10 @@ def frame_coroutine(engine, rank, nranks, max_iterations, halo=8, min_strip_pixe
                 n0, n1 = max(0, a - halo), min(nrows, b + halo)
             engine.pyrup_rows(l, n0, n1)                          # main.cpp:272-279
             engine.convert_rows(l - 1, n0, n1)                    # main.cpp:281
+            mark("prolong L%d->L%d" % (l, l - 1))
     own = (0, sizes[0][0]) if plan[0] is None else plan[0][rank]
     engine.quantise_rows(own[0], own[1])                          # main.cpp:290
+    mark("quantise")
     return plan, own
 
 
@@ -199,6 +205,7 @@ class GpuStripEngine:
         self.depth = [pitched_empty(r, c, torch.float32, self.dev, fill=255.0) for r, c in self.sizes]
         self.depth_u8 = pitched_empty(rows, cols, torch.uint8, self.dev, fill=0)
         self._views = {}
+        self.marks = None            # set to [] to collect (label, event) pairs for one frame
 
     # -- helpers ------------------------------------------------------------------
     @staticmethod
@@ -211,6 +218,16 @@ class GpuStripEngine:
 
     def _ck(self, rc):
         self.ctx._ck(rc)
+
+    def mark(self, label):
+        if self.marks is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(torch.cuda.current_stream(self.dev))
+            self.marks.append((label, ev))
+
+    def phase_ms(self):
+        torch.cuda.synchronize(self.dev)
+        return [(self.marks[i][0], self.marks[i - 1][1].elapsed_time(self.marks[i][1])) for i in range(1, len(self.marks))]
 
     # -- engine interface -----------------------------------------------------------
     def annotation_pyramid(self):

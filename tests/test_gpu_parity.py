@@ -218,7 +218,7 @@ def test_call_order_and_argument_errors(rtdd):
 
 # ---- image processing + pyramid ops -------------------------------------------------------
 
-@pytest.mark.parametrize("rows,cols", [(1, 1), (11, 14), (67, 120), (203, 317)])
+@pytest.mark.parametrize("rows,cols", [(1, 1), (11, 14), (67, 120), (203, 317), (270, 960)])
 def test_image_processing_vs_oracle(rtdd, rows, cols):
     rng = np.random.default_rng(rows * cols)
     ctx = rtdd.DepthDiffusion(max(rows, 2), max(cols, 2), 1)
@@ -247,7 +247,7 @@ def test_image_processing_vs_oracle(rtdd, rows, cols):
     ctx.close()
 
 
-@pytest.mark.parametrize("rows,cols", [(2, 2), (67, 120), (135, 241), (50, 51), (3, 9)])
+@pytest.mark.parametrize("rows,cols", [(2, 2), (67, 120), (135, 241), (50, 51), (3, 9), (270, 480), (33, 1000)])
 def test_pyramid_ops_vs_oracle(rtdd, rows, cols):
     rng = np.random.default_rng(rows + cols)
     ctx = rtdd.DepthDiffusion(rows, cols, 1)

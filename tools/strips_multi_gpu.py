@@ -117,6 +117,10 @@ def main():
             ms, plan, own, exchanges = frame()
             times.append(ms)
         ms = float(np.median(times))
+        eng.marks = []
+        frame()
+        phases = eng.phase_ms()
+        eng.marks = None
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -146,7 +150,7 @@ def main():
                                       % (cols, rows, args.halo),
                           "n_gpus": world, "ms_per_solve": float(t.item()), "Mpixel-sweeps/s": total / (float(t.item()) * 1e-3) / 1e6,
                           "pixel_sweeps": total, "halo_exchanges_per_solve": exchanges, "levels": per, "scaling": "strong",
-                          "bit_identical_to_single_gpu": ok}), flush=True)
+                          "bit_identical_to_single_gpu": ok, "rank0_phase_ms": [[k, round(v, 4)] for k, v in phases]}), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
