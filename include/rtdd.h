@@ -94,6 +94,20 @@ int rtdd_edge_weights(rtdd_ctx *ctx, const float *depth, size_t depthPitch,
  * the number of kernel launches it took. */
 int rtdd_level_sweep_ms(rtdd_ctx *ctx, int level, float *ms, int *iterations, int *kernels);
 
+/* ---- opt-in extensions (NOT the parity path: the reference runs a fixed schedule and never checks convergence,
+ *      ref: src/GPUSolver.cu:226,274-275 accept `tolerance` / `deviceError` and never read them) -------------------- */
+
+/* Max-norm of the last sweep's update, max |x_K - x_{K-1}| over the level, of the most recent solve of `level`:
+ * a warp-shuffle + atomicMax by-product of the final sweep pass (the slot the reference reserved as deviceError).
+ * Blocks until that solve has finished.  *residual is a HOST float. */
+int rtdd_level_residual(rtdd_ctx *ctx, int level, float *residual);
+/* GPUMatrixFreeSolver with the `tolerance` argument honoured: same sweeps, same omega schedule, but the residual is
+ * read back every `checkEvery` sweeps and the level stops early once it is <= tolerance (or at maxIterations).
+ * With tolerance = 0 it runs all maxIterations sweeps and equals rtdd_solve_level bit for bit. */
+int rtdd_solve_level_converge(rtdd_ctx *ctx, float *depth, size_t depthPitch, const uint8_t *scribble, size_t scribblePitch,
+                              const uint8_t *gray, size_t grayPitch, int rows, int cols, int maxIterations, float tolerance,
+                              int checkEvery, int level, int *iterationsRun, float *finalResidual);
+
 /* Self-test of the sweep kernels' branch-free division (csrc/solver_kernels.cu: div_fast) against the
  * compiler's IEEE div.rn (the operation the reference's `sum / count` compiles to, ref: src/GPUSolver.cu:104)
  * on n counter-generated operand pairs.  mode 0 = the whole admitted range, 1 = the sweep's typical range,
@@ -191,6 +205,11 @@ int rtdd_frame_solve_host(rtdd_ctx *ctx, const uint8_t *scribbleHost, size_t scr
 /* Same frame with the annotation planes already on the device (paint with
  * rtdd_frame_paint); nothing crosses PCIe. */
 int rtdd_frame_solve(rtdd_ctx *ctx, int maxIterations);
+/* Warm-start incremental re-solve for live strokes (extension; the reference's only warm start is the coarsest depth
+ * plane persisting between frames, ref: src/main.cpp:257).  Levels coarser than `coarsestLevel` are skipped; level
+ * `coarsestLevel` starts from ITS OWN previous solution with the current annotations re-imposed and runs its scheduled
+ * sweeps; finer levels proceed as in rtdd_frame_solve.  coarsestLevel = levels-1 is exactly rtdd_frame_solve. */
+int rtdd_frame_solve_incremental(rtdd_ctx *ctx, int maxIterations, int coarsestLevel);
 /* ref: src/main.cpp:46-62 -- brush stroke into the context's level-0 annotation planes */
 int rtdd_frame_paint(rtdd_ctx *ctx, int x, int y, int scribbleColor, int scribbleRadius);
 /* device pointers/pitches of the context-owned planes (for effects, tests, downloads) */

@@ -34,6 +34,9 @@ SIGNATURES = {
     "rtdd_solve_level": (i32, [vp, vp, sz, vp, sz, vp, sz, i32, i32, i32, i32]),
     "rtdd_edge_weights": (i32, [vp, vp, sz, vp, sz, i32, i32, i32, vp, vp, sz]),
     "rtdd_level_sweep_ms": (i32, [vp, i32, C.POINTER(f32), C.POINTER(i32), C.POINTER(i32)]),
+    "rtdd_level_residual": (i32, [vp, i32, C.POINTER(f32)]),
+    "rtdd_solve_level_converge": (i32, [vp, vp, sz, vp, sz, vp, sz, i32, i32, i32, f32, i32, i32, C.POINTER(i32), C.POINTER(f32)]),
+    "rtdd_frame_solve_incremental": (i32, [vp, i32, i32]),
     "rtdd_selftest_division": (i32, [vp, C.c_ulonglong, C.c_ulonglong, i32, C.POINTER(C.c_ulonglong)]),
     "rtdd_strip_init": (i32, [vp, i32, vp, sz, vp, sz, vp, sz, i32, i32, i32, i32]),
     "rtdd_strip_pass": (i32, [vp, i32, i32, i32, i32]),

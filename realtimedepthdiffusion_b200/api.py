@@ -128,6 +128,23 @@ class DepthDiffusion:
         self._ck(lib.rtdd_level_sweep_ms(self._h, int(level), C.byref(ms), C.byref(it), C.byref(k)))
         return ms.value, it.value, k.value
 
+    def level_residual(self, level):
+        r = C.c_float()
+        self._ck(lib.rtdd_level_residual(self._h, int(level), C.byref(r)))
+        return r.value
+
+    def matrix_free_solver_converge(self, depth, scribble, gray, max_iterations, tolerance, level, check_every=8):
+        """Extension: GPUMatrixFreeSolver honouring `tolerance`.  Returns (sweeps run, final residual)."""
+        rows, cols = depth.shape
+        it, res = C.c_int(), C.c_float()
+        self._ck(lib.rtdd_solve_level_converge(self._h, _ptr(depth), _pitch(depth), _ptr(scribble), _pitch(scribble), _ptr(gray), _pitch(gray),
+                                               rows, cols, int(max_iterations), float(tolerance), int(check_every), int(level),
+                                               C.byref(it), C.byref(res)))
+        return it.value, res.value
+
+    def frame_solve_incremental(self, max_iterations, coarsest_level):
+        self._ck(lib.rtdd_frame_solve_incremental(self._h, int(max_iterations), int(coarsest_level)))
+
     def selftest_division(self, n, seed=1, mode=0):
         mism = C.c_ulonglong(0)
         self._ck(lib.rtdd_selftest_division(self._h, int(n), int(seed), int(mode), C.byref(mism)))

@@ -221,12 +221,13 @@ int enqueue_level(rtdd_ctx *ctx, cudaStream_t s, const LevelArgs &a, bool captur
     int plane = 0;
     bool direct = false;
     if (a.iters > 0) {
-        rtdd::SweepTarget tgt = {a.depth, (int)(a.depthPitch / sizeof(float)), a.u8, (int)a.u8Pitch};
         direct = target_ok(a.depth, a.depthPitch);
+        rtdd::SweepTarget tgt = {direct ? a.depth : nullptr, (int)(a.depthPitch / sizeof(float)), direct ? a.u8 : nullptr, (int)a.u8Pitch, L.dResidual};
+        RTDD_TRY(cudaMemsetAsync(L.dResidual, 0, sizeof(unsigned int), s), "residual reset");
         const unsigned int flags = capturing ? cudaEventRecordExternal : cudaEventRecordDefault;
         RTDD_TRY(cudaEventRecordWithFlags(L.evBegin, s, flags), "level event");
         int k = 0;
-        int rc = enqueue_sweeps(ctx, s, a.level, a.iters, direct ? &tgt : nullptr, &k, &plane);
+        int rc = enqueue_sweeps(ctx, s, a.level, a.iters, &tgt, &k, &plane);
         if (rc) return rc;
         RTDD_TRY(cudaEventRecordWithFlags(L.evEnd, s, flags), "level event");
         L.timed = true; L.lastIters = a.iters; L.lastKernels = k;
@@ -323,7 +324,7 @@ int rtdd_create(int rows, int cols, int levels, int device, rtdd_ctx **out)
 
     // one arena: per level 4 float planes + 3 byte planes, each with a guard row above and below
     ctx->lv.resize(levels);
-    size_t total = 257 * sizeof(float) + 256;
+    size_t total = 257 * sizeof(float) + 256 + 256;      // LUT + one residual word per level (<= 30 levels)
     for (int l = 0; l < levels; l++) {
         RtddLevel &L = ctx->lv[l];
         // ref: src/GPUSolver.cu:42-43 -- int rowsPerLevel = rows / powf(2, level)
@@ -342,8 +343,11 @@ int rtdd_create(int rows, int cols, int levels, int device, rtdd_ctx **out)
     char *p = (char *)ctx->arena;
     ctx->dLut = (float *)p;
     p += rtdd_round_up(257 * sizeof(float), 256);
+    unsigned int *resWords = (unsigned int *)p;
+    p += 256;
     for (int l = 0; l < levels; l++) {
         RtddLevel &L = ctx->lv[l];
+        L.dResidual = resWords + l;
         for (int k = 0; k < 4; k++) { L.x[k] = (float *)p; p += rtdd_round_up((size_t)L.pitchF * L.rows * sizeof(float), 256); }
         L.linkR = (uint8_t *)p; p += rtdd_round_up((size_t)L.pitchB * L.rows, 256);
         L.linkD = (uint8_t *)p; p += rtdd_round_up((size_t)L.pitchB * L.rows, 256);
@@ -510,6 +514,47 @@ int rtdd_level_sweep_ms(rtdd_ctx *ctx, int level, float *ms, int *iterations, in
     return 0;
 }
 
+int rtdd_level_residual(rtdd_ctx *ctx, int level, float *residual)
+{
+    if (!ctx) return RTDD_E_ARG;
+    if (level < 0 || level >= ctx->levels || !residual) return rtdd_fail(ctx, RTDD_E_ARG, "rtdd_level_residual");
+    DeviceGuard guard(ctx->device);
+    unsigned int bits = 0;
+    RTDD_TRY(cudaMemcpyAsync(&bits, ctx->lv[level].dResidual, sizeof(bits), cudaMemcpyDeviceToHost, ctx->stream), "rtdd_level_residual");
+    RTDD_TRY(cudaStreamSynchronize(ctx->stream), "rtdd_level_residual");
+    memcpy(residual, &bits, sizeof(bits));
+    return 0;
+}
+
+int rtdd_solve_level_converge(rtdd_ctx *ctx, float *depth, size_t depthPitch, const uint8_t *scribble, size_t scribblePitch,
+                              const uint8_t *gray, size_t grayPitch, int rows, int cols, int maxIterations, float tolerance,
+                              int checkEvery, int level, int *iterationsRun, float *finalResidual)
+{
+    if (!ctx) return RTDD_E_ARG;
+    if (maxIterations < 0 || checkEvery < 1 || !(tolerance >= 0.0f)) return rtdd_fail(ctx, RTDD_E_ARG, "rtdd_solve_level_converge");
+    int rc = rtdd_strip_init(ctx, level, depth, depthPitch, scribble, scribblePitch, gray, grayPitch, rows, cols, 0, rows);
+    if (rc) return rc;
+    const int T = 8;
+    int done = 0;
+    float res = INFINITY;
+    while (done < maxIterations) {
+        int chunk = maxIterations - done < checkEvery ? maxIterations - done : checkEvery;
+        while (chunk > 0) {
+            const int n = chunk < T ? chunk : T;
+            rc = rtdd_strip_pass(ctx, level, done, n, T);
+            if (rc) return rc;
+            done += n;
+            chunk -= n;
+        }
+        rc = rtdd_level_residual(ctx, level, &res);          // one 4-byte read-back per check
+        if (rc) return rc;
+        if (res <= tolerance) break;
+    }
+    if (iterationsRun) *iterationsRun = done;
+    if (finalResidual) *finalResidual = res;
+    return rtdd_strip_finish(ctx, level, depth, depthPitch, 0, rows);
+}
+
 int rtdd_edge_weights(rtdd_ctx *ctx, const float *depth, size_t depthPitch, const uint8_t *gray, size_t grayPitch,
                       int rows, int cols, int level, uint8_t *linkRight, uint8_t *linkDown, size_t outPitch)
 {
@@ -572,8 +617,11 @@ int rtdd_strip_pass(rtdd_ctx *ctx, int level, int firstSweep, int nsweeps, int h
     RtddLevel W = L;
     W.rows = L.stripRows;
     const int src = L.stripPair, dst = src ^ 2;
+    // the residual of this pass's last sweep (over the whole window; stale ghost rows can only raise it)
+    const rtdd::SweepTarget tgt = {nullptr, 0, nullptr, 0, L.dResidual};
+    RTDD_TRY(cudaMemsetAsync(L.dResidual, 0, sizeof(unsigned int), ctx->stream), "rtdd_strip_pass");
     RTDD_TRY(rtdd::launch_sweep_blocked(ctx->stream, W, ctx->dLut, L.x[src], L.x[src + 1], L.x[dst], L.x[dst + 1], pack, haloT, nsweeps, 0.99f,
-                                        firstSweep == 0, ctx->smCount), "rtdd_strip_pass");
+                                        firstSweep == 0, ctx->smCount, &tgt), "rtdd_strip_pass");
     ctx->launches++;
     L.stripPair = dst;
     return 0;
@@ -847,21 +895,21 @@ int rtdd_frame_set_image(rtdd_ctx *ctx, const uint8_t *bgrHost, size_t bgrPitch)
     return 0;
 }
 
-int rtdd_frame_solve(rtdd_ctx *ctx, int maxIterations)
+static int frame_solve_from(rtdd_ctx *ctx, int maxIterations, int startLevel)
 {
     if (!ctx) return RTDD_E_ARG;
     if (!ctx->imageSet || !ctx->lutLoaded) return rtdd_fail(ctx, RTDD_E_STATE, "rtdd_frame_solve");
-    if (maxIterations < 0) return rtdd_fail(ctx, RTDD_E_ARG, "rtdd_frame_solve");
+    if (maxIterations < 0 || startLevel < 0 || startLevel >= ctx->levels) return rtdd_fail(ctx, RTDD_E_ARG, "rtdd_frame_solve");
     DeviceGuard guard(ctx->device);
     int rc = ensure_omega_table(ctx, maxIterations);
     if (rc) return rc;
     // the whole frame is ONE graph launch: every plane it touches is owned by the context, so the graph never goes stale
     RtddGraphKey key{};
-    key.kind = 2; key.iters = maxIterations; key.variant = ctx->variant; key.T = ctx->sweepsPerPass;
+    key.kind = 2; key.level = startLevel; key.iters = maxIterations; key.variant = ctx->variant; key.T = ctx->sweepsPerPass;
     return run_cached_graph(ctx, key, [&](cudaStream_t cs, int *kernels) -> int {
-        const int Lc = ctx->levels - 1;
+        const int Lc = startLevel;          // coarsest level that is (re)solved; it starts from its current depth plane
         int n = 0;
-        for (int l = 1; l < ctx->levels; l++) {                               // main.cpp:249
+        for (int l = 1; l <= Lc; l++) {                                       // main.cpp:249
             RtddFrameLevel &P = ctx->fl[l - 1], &F = ctx->fl[l];
             RTDD_TRY(rtdd::launch_pyrdown_annotation(cs, P.scribble, P.scribblePitch, P.edited, P.editedPitch, P.rows, P.cols,
                                                      F.scribble, F.scribblePitch, F.edited, F.editedPitch, F.rows, F.cols), "frame: annotation");
@@ -892,6 +940,18 @@ int rtdd_frame_solve(rtdd_ctx *ctx, int maxIterations)
         *kernels = n;
         return 0;
     });
+}
+
+int rtdd_frame_solve(rtdd_ctx *ctx, int maxIterations)
+{
+    if (!ctx) return RTDD_E_ARG;
+    return frame_solve_from(ctx, maxIterations, ctx->levels - 1);
+}
+
+int rtdd_frame_solve_incremental(rtdd_ctx *ctx, int maxIterations, int coarsestLevel)
+{
+    if (!ctx) return RTDD_E_ARG;
+    return frame_solve_from(ctx, maxIterations, coarsestLevel);
 }
 
 int rtdd_frame_solve_host(rtdd_ctx *ctx, const uint8_t *scribbleHost, size_t scribblePitch,

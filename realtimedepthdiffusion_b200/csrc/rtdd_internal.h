@@ -33,6 +33,7 @@ struct RtddLevel {
     int lastIters = 0, lastKernels = 0;
     // row-strip mode (rtdd_strip_*): the level's planes hold rows [stripBegin, stripBegin + stripRows) of the level
     int stripBegin = 0, stripRows = 0, stripPair = 0;
+    unsigned int *dResidual = nullptr;   // bits of the max-norm of the last sweep's update (rtdd_level_residual)
 };
 
 // Context-owned images of the frame driver (what main.cpp keeps in GpuMat vectors).
@@ -106,8 +107,9 @@ namespace rtdd {
 // A caller-visible destination for the LAST sweep pass of a level: the pitched depth plane (16-byte aligned rows)
 // and optionally the 8-bit quantised map.  Null = the library's own planes.
 struct SweepTarget {
-    float *x; int pitchX;        // floats per row
+    float *x; int pitchX;        // floats per row; null = keep the library's own planes
     uint8_t *u8; int pitchU8;    // may be null
+    unsigned int *res;           // may be null: receives the bits of max |x_K - x_{K-1}| (atomicMax)
 };
 cudaError_t launch_level_init(cudaStream_t s, const RtddLevel &L, const float *depth, size_t depthPitch,
                               const uint8_t *scribble, size_t scribblePitch,

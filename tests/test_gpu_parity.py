@@ -481,3 +481,70 @@ def test_strip_decomposition_on_one_gpu_is_bit_identical(rtdd, rows, cols, nrank
     assert np.array_equal(got_u8, want_u8)
     for e in engines:
         e.ctx.close()
+
+
+# ---- opt-in extensions: residual, tolerance-driven early exit, warm-start incremental re-solve ------------------
+
+@pytest.mark.parametrize("rows,cols,level,levels", [(67, 120, 0, 1), (203, 317, 0, 2), (300, 700, 1, 2), (600, 1100, 0, 2)])
+def test_residual_is_the_max_norm_of_the_last_update(rtdd, rows, cols, level, levels):
+    iters = 21
+    gray, depth, scribble = random_level(rows, cols, 77 + rows)
+    a = ob.solve_level(depth, scribble, gray, iters - 1, level, levels - 1)
+    b = ob.solve_level(depth, scribble, gray, iters, level, levels - 1)
+    want = np.abs(b - a).max()
+    for variant, T in ((1, 0), (2, 8), (2, 5), (3, 0), (0, 0)):
+        ctx = rtdd.DepthDiffusion(rows << level, cols << level, levels)
+        ctx.set_sweep_variant(variant, T)
+        d, s, g = to_dev(depth), to_dev(scribble), to_dev(gray)
+        ctx.matrix_free_solver(d, s, g, iters, level)
+        assert ctx.level_residual(level) == np.float32(want), (variant, T)
+        ctx.close()
+
+
+def test_tolerance_driven_solve_matches_fixed_schedule_prefix(rtdd):
+    rows, cols = 270, 480
+    gray, depth, scribble = random_level(rows, cols, 91)
+    ctx = rtdd.DepthDiffusion(rows, cols, 1)
+    d, s, g = to_dev(depth), to_dev(scribble), to_dev(gray)
+    n, res = ctx.matrix_free_solver_converge(d, s, g, 120, 0.0, 0, check_every=16)
+    assert n == 120
+    assert np.array_equal(to_host(d).view(np.uint32), ob.solve_level(depth, scribble, gray, 120, 0, 0).view(np.uint32))
+    d2 = to_dev(depth)
+    n2, res2 = ctx.matrix_free_solver_converge(d2, s, g, 1000, 0.5, 0, check_every=16)
+    assert 16 <= n2 < 1000 and n2 % 16 == 0 and res2 <= 0.5
+    assert np.array_equal(to_host(d2).view(np.uint32), ob.solve_level(depth, scribble, gray, n2, 0, 0).view(np.uint32))
+    ctx.close()
+
+
+def test_incremental_frame_solve(rtdd):
+    rows, cols, iters = 540, 960, 1000
+    bgr, scribble, edited = synth.synth_case(rows, cols, 555)
+    out = np.zeros((rows, cols), np.uint8)
+    full = rtdd.DepthDiffusion(rows, cols)
+    full.frame_set_image(bgr)
+    full.frame_solve_host(scribble, edited, iters, out)
+    inc = rtdd.DepthDiffusion(rows, cols)
+    inc.frame_set_image(bgr)
+    inc.frame_solve_host(scribble, edited, iters, out)
+    # coarsest_level = levels-1 is the full frame
+    inc.frame_solve_incremental(iters, inc.levels - 1)
+    full.frame_solve(iters)
+    a = full.frame_plane(full.PLANE_DEPTH, 0).cpu().numpy()
+    b = inc.frame_plane(inc.PLANE_DEPTH, 0).cpu().numpy()
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    # a new stroke, re-solved from level 1 downwards on top of the previous solution
+    for e in synth.brush_events(rows, cols, 9, 1, 6):
+        full.frame_paint(*e)
+        inc.frame_paint(*e)
+    full.frame_solve(iters)
+    inc.frame_solve_incremental(iters, 1)
+    a = full.frame_plane(full.PLANE_DEPTH, 0).cpu().numpy()
+    b = inc.frame_plane(inc.PLANE_DEPTH, 0).cpu().numpy()
+    s = inc.frame_plane(inc.PLANE_SCRIBBLE, 0).cpu().numpy()
+    e = inc.frame_plane(inc.PLANE_EDITED, 0).cpu().numpy().reshape(rows, cols, 3)
+    assert np.array_equal(b[s == 255], e[..., 0][s == 255].astype(np.float32))      # Dirichlet values re-imposed
+    assert np.isfinite(b).all()
+    # an approximation, not parity: it must stay in the neighbourhood of the full solve
+    assert np.abs(a - b).mean() < 8.0
+    full.close()
+    inc.close()

@@ -1,0 +1,53 @@
+"""BASELINE configs[1]: 1920x1080 synthetic image, a sequence of brush strokes, one solve frame per stroke.
+Reports ms/frame for the parity path (full fixed-schedule solve, as main.cpp --live does) and for the opt-in
+warm-start incremental re-solve, with the quality delta of the latter against the former.
+python tools/live_strokes.py [strokes] > gpurun_out/live.json"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import realtimedepthdiffusion_b200 as rtdd          # noqa: E402
+from realtimedepthdiffusion_b200 import synth       # noqa: E402
+
+rows, cols, seed = 1080, 1920, 1002
+nstrokes = int(sys.argv[1]) if len(sys.argv) > 1 else 32
+bgr, scribble, edited = synth.synth_case(rows, cols, seed, strokes=8)
+events = synth.brush_events(rows, cols, seed + 1, nstrokes, 1)          # one brush event per stroke frame
+out = np.zeros((rows, cols), np.uint8)
+res = {"workload": "configs[1]: 1920x1080 synthetic image, %d live brush events, one solve frame per event" % nstrokes}
+ctxs = {}
+for mode in ("parity", "incremental_L2", "incremental_L1"):
+    ctx = rtdd.DepthDiffusion(rows, cols)
+    ctx.frame_set_image(bgr)
+    ctx.frame_solve_host(scribble, edited, 1000, out)
+    ctxs[mode] = ctx
+ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+times = {m: [] for m in ctxs}
+delta = {m: [] for m in ctxs}
+ident = {m: [] for m in ctxs}
+for (x, y, colour, radius) in events:
+    for mode, ctx in ctxs.items():
+        ev0.record()
+        ctx.frame_paint(x, y, colour, radius)
+        if mode == "parity":
+            ctx.frame_solve(1000)
+        else:
+            ctx.frame_solve_incremental(1000, int(mode[-1]))
+        ev1.record()
+        ev1.synchronize()
+        times[mode].append(ev0.elapsed_time(ev1))
+    ref = ctxs["parity"].frame_plane(0, 0)
+    refq = ctxs["parity"].frame_plane(5, 0)
+    for mode, ctx in ctxs.items():
+        d = ctx.frame_plane(0, 0)
+        delta[mode].append(float((d - ref).abs().mean()))
+        ident[mode].append(float((ctx.frame_plane(5, 0) == refq).float().mean()))
+for mode in ctxs:
+    res[mode] = {"ms_per_frame_median": float(np.median(times[mode])), "mean_abs_depth_delta_vs_parity": float(np.mean(delta[mode])),
+                 "identical_8bit_fraction_vs_parity": float(np.mean(ident[mode]))}
+print(json.dumps(res))
