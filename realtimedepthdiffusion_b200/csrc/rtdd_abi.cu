@@ -427,6 +427,20 @@ int rtdd_set_tuning(rtdd_ctx *ctx, const char *key, int value)
         destroy_graphs(ctx);
         return 0;
     }
+    if (strcmp(key, "resident_warps") == 0 && value >= 1 && value <= 32) {
+        rtdd::set_resident_warps(value);
+        DeviceGuard guard(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+        destroy_graphs(ctx);
+        return 0;
+    }
+    if (strcmp(key, "resident_two_sweep") == 0 && (value == 0 || value == 1)) {
+        rtdd::set_resident_two_sweep(value);
+        DeviceGuard guard(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+        destroy_graphs(ctx);
+        return 0;
+    }
     if (strcmp(key, "blocked_tma") == 0 && (value == 0 || value == 1)) {
         rtdd::set_blocked_tma(value);
         DeviceGuard guard(ctx->device);

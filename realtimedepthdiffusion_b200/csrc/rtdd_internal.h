@@ -125,6 +125,8 @@ cudaError_t launch_sweep_blocked(cudaStream_t s, const RtddLevel &L, const float
 int blocked_max_T();
 void set_blocked_tile_override(int tile);
 void set_blocked_tma(int enabled);
+void set_resident_warps(int w);
+void set_resident_two_sweep(int on);
 // resident (one cluster, all sweeps in one launch); omegas = device array of nsweeps floats
 bool resident_plan(int rows, int cols, int *R, int *clusterSize, int *blocksPerCta, int *WX);
 cudaError_t launch_sweep_resident(cudaStream_t s, const RtddLevel &L, const float *lut, const float *x, float *xOut,
