@@ -34,7 +34,7 @@ if ROOT not in sys.path:
 
 WORKLOADS = {"4k": (2160, 3840, 1003), "1080p": (1080, 1920, 1002), "720p": (720, 1280, 1001), "tiny": (203, 317, 77)}
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE level-0 launch (ncu --set full, profiles/r01_ncu_sweep_blocked_L0.txt)
-NCU_TRAFFIC_BYTES_PER_LAUNCH = {"4k": 84.8e6}
+NCU_TRAFFIC_BYTES_PER_LAUNCH = {"4k": 132.0e6}
 BYTES_PER_PIXEL_SWEEP = 17.0     # x_k 4 + x_{k-1} 4 + x_{k+1} 4 + 4 link indices 4 + mask 1
 
 
@@ -274,7 +274,7 @@ def run_native(args, dist, rank, world, local):
                      "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH.get(args.workload), "algorithmic_bytes_per_launch": BYTES_PER_PIXEL_SWEEP * r0 * c0 * it0 / k0,
                      "avg_launch_ms": l0 / k0,
                      "note": "achieved = 17 B x pixel-sweeps / time is the EFFECTIVE sweep bandwidth (SURVEY.md 8d): the kernel is temporally "
-                             "blocked (8 sweeps per HBM round trip), so its real DRAM traffic (`traffic`, ncu) is ~13x below the algorithmic "
+                             "blocked (8 sweeps per HBM round trip), so its real DRAM traffic (`traffic`, ncu) is ~8.5x below the algorithmic "
                              "bytes and frac may exceed 1; the kernel is issue-bound, not HBM-bound (profiles/r01_ncu_*.txt)"},
         "levels": [{"level": l, "size": "%dx%d" % (per_level[l][1], per_level[l][0]), "sweeps": per_level[l][2], "ms": lvl_ms[l][0],
                     "launches": lvl_ms[l][2], "us_per_sweep": 1e3 * lvl_ms[l][0] / max(per_level[l][2], 1),
