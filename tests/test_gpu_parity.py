@@ -349,13 +349,13 @@ def have_ref():
 
 
 @pytest.mark.skipif(not have_ref(), reason="oracle/_ref/libref.so not built")
-@pytest.mark.parametrize("name", ["synth_tiny", "synth_odd", "dog"])
+@pytest.mark.parametrize("name", ["synth_tiny", "synth_odd", "dog", "womanparasol"])
 def test_main_loop_ab_reference_vs_shims(name):
     """The same restated main.cpp loop, once over the reference's functions and once over ours."""
     from realtimedepthdiffusion_b200 import _native
     from tests.test_oracle_cpu import _load_case
     bgr, scribble, edited = _load_case(name)
-    iters = {"dog": 1000, "synth_odd": 200, "synth_tiny": 60}[name]
+    iters = {"dog": 1000, "womanparasol": 1000, "synth_odd": 200, "synth_tiny": 60}[name]
     res = {}
     for tag, api in (("ref", ob.ref_api()), ("new", _native.shims)):
         loop = MainLoop(api, bgr)
@@ -428,7 +428,7 @@ def test_frame_solve_host_vs_oracle(rtdd, rows, cols, iters):
 
 # ---- golden vectors recorded from the reference on a B200 ---------------------------------------
 
-@pytest.mark.parametrize("name", ["synth_tiny", "synth_small", "synth_odd", "dog"])
+@pytest.mark.parametrize("name", ["synth_tiny", "synth_small", "synth_odd", "dog", "womanparasol"])
 def test_shims_reproduce_reference_golden(name):
     path = os.path.join(GOLD, "ref_solver_%s.npz" % name)
     if not os.path.exists(path):

@@ -142,8 +142,8 @@ def _golden(pattern):
 
 
 def _load_case(name):
-    if name == "dog":
-        z = np.load(os.path.join(GOLD, "inputs_dog.npz"))
+    if name in ("dog", "womanparasol"):
+        z = np.load(os.path.join(GOLD, "inputs_%s.npz" % name))
         bgr, ann = z["bgr"], z["annotation"]
         scribble = np.where(ann != 32, 255, 0).astype(np.uint8)
         edited = bgr.copy()
@@ -153,7 +153,7 @@ def _load_case(name):
     return synth.synth_case(*cases[name])
 
 
-@pytest.mark.parametrize("name", ["synth_tiny", "synth_small", "synth_odd", "dog"])
+@pytest.mark.parametrize("name", ["synth_tiny", "synth_small", "synth_odd", "dog", "womanparasol"])
 def test_oracle_reproduces_reference_solver_golden(name):
     path = os.path.join(GOLD, "ref_solver_%s.npz" % name)
     if not os.path.exists(path):

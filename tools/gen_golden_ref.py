@@ -29,8 +29,8 @@ def sha(a):
 
 
 def load_case(name):
-    if name == "dog":
-        z = np.load(os.path.join(ROOT, "tests", "golden", "inputs_dog.npz"))
+    if name in ("dog", "womanparasol"):
+        z = np.load(os.path.join(ROOT, "tests", "golden", "inputs_%s.npz" % name))
         bgr, ann = z["bgr"], z["annotation"]
         scribble = np.where(ann != 32, 255, 0).astype(np.uint8)           # main.cpp:163-168
         edited = bgr.copy()
@@ -128,7 +128,10 @@ def main():
     api = ob.ref_api()
     libref = C.CDLL(ob.LIBREF)    # same handle dlopen returns again (already loaded)
     dog = None
-    for name, iters in (("dog", 1000), ("synth_odd", 200), ("synth_small", 120), ("synth_tiny", 60)):
+    only = sys.argv[1:]
+    for name, iters in (("dog", 1000), ("womanparasol", 1000), ("synth_odd", 200), ("synth_small", 120), ("synth_tiny", 60)):
+        if only and name not in only:
+            continue
         rec, bgr, gray, depth0 = solver_case(api, name, iters)
         np.savez_compressed(os.path.join(OUT, "ref_solver_%s.npz" % name), **rec)
         print("solver", name, "levels", int(rec["levels"]), flush=True)
@@ -138,6 +141,9 @@ def main():
             print("effects", name, flush=True)
         if name == "dog":
             dog = (bgr, gray, depth0)
+    if only:
+        print("golden written to", OUT)
+        return
     # effects on Dog: u8 outputs only (depth is reproducible from the solver golden via sha)
     eff = effects_case(api, *dog)
     np.savez_compressed(os.path.join(OUT, "ref_effects_dog.npz"), **compact_effects(sha(dog[2]), eff))
