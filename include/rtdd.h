@@ -141,6 +141,20 @@ int rtdd_strip_init(rtdd_ctx *ctx, int level, const float *depth, size_t depthPi
 int rtdd_strip_pass(rtdd_ctx *ctx, int level, int firstSweep, int nsweeps, int haloT);
 int rtdd_strip_planes(rtdd_ctx *ctx, int level, float **xk, float **xkm1, size_t *pitchBytes, int *winBegin, int *winRows);
 int rtdd_strip_finish(rtdd_ctx *ctx, int level, float *depth, size_t depthPitch, int rowBegin, int rowEnd);
+/* Fused halo exchange: instead of handing the halo rows to NCCL, the sweep pass itself stores the rows next to a strip
+ * boundary into the neighbouring rank's ghost rows (peer memory, NVLink) and raises a flag there; the neighbour's
+ * next pass waits for that flag on the device.  Every rank's arena has the same layout, so a neighbour is described
+ * by the base of its arena: rtdd_ipc_export / rtdd_ipc_import move a CUDA IPC handle (64 bytes) between processes
+ * (rtdd_arena gives the base directly for contexts of one process).  rtdd_strip_neighbours, called after
+ * rtdd_strip_init, gives this rank's own rows [ownBegin, ownEnd), the halo depth and the first row of the windows of
+ * the ranks above / below (-1 = none) and switches the level to the fused mode; rtdd_strip_wait enqueues the wait for
+ * the neighbours' LAST pass (needed before rtdd_strip_finish / prolongation read the ghost rows). */
+int rtdd_ipc_export(rtdd_ctx *ctx, void *handle64);
+int rtdd_ipc_import(rtdd_ctx *ctx, const void *handle64, void **peerArena);
+int rtdd_arena(rtdd_ctx *ctx, void **base, size_t *bytes);
+int rtdd_strip_set_peers(rtdd_ctx *ctx, void *arenaAbove, void *arenaBelow);
+int rtdd_strip_neighbours(rtdd_ctx *ctx, int level, int ownBegin, int ownEnd, int halo, int aboveWinBegin, int belowWinBegin);
+int rtdd_strip_wait(rtdd_ctx *ctx, int level);
 /* cv::pyrUp restricted to destination rows [rowBegin, rowEnd); src and dst are the full planes */
 int rtdd_pyrup_depth_rows(rtdd_ctx *ctx, const float *src, size_t srcPitch, int srcRows, int srcCols,
                           float *dst, size_t dstPitch, int dstRows, int dstCols, int rowBegin, int rowEnd);

@@ -42,6 +42,12 @@ SIGNATURES = {
     "rtdd_strip_pass": (i32, [vp, i32, i32, i32, i32]),
     "rtdd_strip_planes": (i32, [vp, i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(sz), C.POINTER(i32), C.POINTER(i32)]),
     "rtdd_strip_finish": (i32, [vp, i32, vp, sz, i32, i32]),
+    "rtdd_ipc_export": (i32, [vp, vp]),
+    "rtdd_ipc_import": (i32, [vp, vp, C.POINTER(vp)]),
+    "rtdd_arena": (i32, [vp, C.POINTER(vp), C.POINTER(sz)]),
+    "rtdd_strip_set_peers": (i32, [vp, vp, vp]),
+    "rtdd_strip_neighbours": (i32, [vp, i32, i32, i32, i32, i32, i32]),
+    "rtdd_strip_wait": (i32, [vp, i32]),
     "rtdd_pyrup_depth_rows": (i32, [vp, vp, sz, i32, i32, vp, sz, i32, i32, i32, i32]),
     "rtdd_set_tuning": (i32, [vp, C.c_char_p, i32]),
     "rtdd_set_sweep_variant": (i32, [vp, i32, i32]),

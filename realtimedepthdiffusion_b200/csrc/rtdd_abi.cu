@@ -324,7 +324,7 @@ int rtdd_create(int rows, int cols, int levels, int device, rtdd_ctx **out)
 
     // one arena: per level 4 float planes + 3 byte planes, each with a guard row above and below
     ctx->lv.resize(levels);
-    size_t total = 257 * sizeof(float) + 256 + 256;      // LUT + one residual word per level (<= 30 levels)
+    size_t total = 257 * sizeof(float) + 256 + 256 + 2048;   // LUT + one residual word per level (<= 30 levels) + strip tickets/flags
     for (int l = 0; l < levels; l++) {
         RtddLevel &L = ctx->lv[l];
         // ref: src/GPUSolver.cu:42-43 -- int rowsPerLevel = rows / powf(2, level)
@@ -345,9 +345,12 @@ int rtdd_create(int rows, int cols, int levels, int device, rtdd_ctx **out)
     p += rtdd_round_up(257 * sizeof(float), 256);
     unsigned int *resWords = (unsigned int *)p;
     p += 256;
+    unsigned int *stripWords = (unsigned int *)p;      // 16 words per level (same offset in every rank's arena)
+    p += 2048;
     for (int l = 0; l < levels; l++) {
         RtddLevel &L = ctx->lv[l];
         L.dResidual = resWords + l;
+        L.dStripWords = stripWords + 16 * l;
         for (int k = 0; k < 4; k++) { L.x[k] = (float *)p; p += rtdd_round_up((size_t)L.pitchF * L.rows * sizeof(float), 256); }
         L.linkR = (uint8_t *)p; p += rtdd_round_up((size_t)L.pitchB * L.rows, 256);
         L.linkD = (uint8_t *)p; p += rtdd_round_up((size_t)L.pitchB * L.rows, 256);
@@ -613,6 +616,74 @@ int rtdd_strip_init(rtdd_ctx *ctx, int level, const float *depth, size_t depthPi
                                      gray + (size_t)winBegin * grayPitch, grayPitch, coarsest, threshold, L.x[0]), "rtdd_strip_init");
     ctx->launches++;
     L.stripBegin = winBegin; L.stripRows = W.rows; L.stripPair = 0;
+    L.stripFused = false;
+    L.stripFirstPassAbs = L.stripPassAbs;
+    return 0;
+}
+
+int rtdd_ipc_export(rtdd_ctx *ctx, void *handle64)
+{
+    if (!ctx) return RTDD_E_ARG;
+    if (!handle64) return rtdd_fail(ctx, RTDD_E_ARG, "rtdd_ipc_export");
+    DeviceGuard guard(ctx->device);
+    cudaIpcMemHandle_t h;
+    static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    RTDD_TRY(cudaIpcGetMemHandle(&h, ctx->arena), "rtdd_ipc_export");
+    memcpy(handle64, &h, sizeof(h));
+    return 0;
+}
+
+int rtdd_ipc_import(rtdd_ctx *ctx, const void *handle64, void **peerArena)
+{
+    if (!ctx) return RTDD_E_ARG;
+    if (!handle64 || !peerArena) return rtdd_fail(ctx, RTDD_E_ARG, "rtdd_ipc_import");
+    DeviceGuard guard(ctx->device);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof(h));
+    const int rc = rtdd_check(ctx, cudaIpcOpenMemHandle(peerArena, h, cudaIpcMemLazyEnablePeerAccess), "rtdd_ipc_import");
+    return rc ? rtdd_fail(ctx, RTDD_E_PEER, "rtdd_ipc_import (cudaIpcOpenMemHandle)") : 0;
+}
+
+int rtdd_arena(rtdd_ctx *ctx, void **base, size_t *bytes)
+{
+    if (!ctx) return RTDD_E_ARG;
+    if (base) *base = ctx->arena;
+    if (bytes) *bytes = ctx->arenaBytes;
+    return 0;
+}
+
+int rtdd_strip_set_peers(rtdd_ctx *ctx, void *arenaAbove, void *arenaBelow)
+{
+    if (!ctx) return RTDD_E_ARG;
+    ctx->peerUp = (char *)arenaAbove;
+    ctx->peerDn = (char *)arenaBelow;
+    return 0;
+}
+
+int rtdd_strip_neighbours(rtdd_ctx *ctx, int level, int ownBegin, int ownEnd, int halo, int aboveWinBegin, int belowWinBegin)
+{
+    if (!ctx) return RTDD_E_ARG;
+    if (level < 0 || level >= ctx->levels) return rtdd_fail(ctx, RTDD_E_ARG, "rtdd_strip_neighbours");
+    RtddLevel &L = ctx->lv[level];
+    if (L.stripRows <= 0 || ownBegin < L.stripBegin || ownEnd > L.stripBegin + L.stripRows || ownEnd - ownBegin < halo || halo < 1)
+        return rtdd_fail(ctx, RTDD_E_ARG, "rtdd_strip_neighbours");
+    L.stripOwnBegin = ownBegin; L.stripOwnEnd = ownEnd; L.stripHalo = halo;
+    L.stripUpWinBegin = aboveWinBegin; L.stripDnWinBegin = belowWinBegin;
+    L.stripFused = true;
+    return 0;
+}
+
+int rtdd_strip_wait(rtdd_ctx *ctx, int level)
+{
+    if (!ctx) return RTDD_E_ARG;
+    if (level < 0 || level >= ctx->levels) return rtdd_fail(ctx, RTDD_E_ARG, "rtdd_strip_wait");
+    RtddLevel &L = ctx->lv[level];
+    if (!L.stripFused || L.stripPassAbs == L.stripFirstPassAbs) return 0;
+    DeviceGuard guard(ctx->device);
+    const unsigned int *wu = (ctx->peerUp && L.stripUpWinBegin >= 0) ? L.dStripWords + 1 : nullptr;
+    const unsigned int *wd = (ctx->peerDn && L.stripDnWinBegin >= 0) ? L.dStripWords + 2 : nullptr;
+    RTDD_TRY(rtdd::launch_halo_wait(ctx->stream, wu, wd, L.stripPassAbs), "rtdd_strip_wait");
+    ctx->launches++;
     return 0;
 }
 
@@ -634,8 +705,42 @@ int rtdd_strip_pass(rtdd_ctx *ctx, int level, int firstSweep, int nsweeps, int h
     // the residual of this pass's last sweep (over the whole window; stale ghost rows can only raise it)
     const rtdd::SweepTarget tgt = {nullptr, 0, nullptr, 0, L.dResidual};
     RTDD_TRY(cudaMemsetAsync(L.dResidual, 0, sizeof(unsigned int), ctx->stream), "rtdd_strip_pass");
+    rtdd::HaloPush hp = {};
+    const bool fused = L.stripFused && (ctx->peerUp || ctx->peerDn);
+    if (fused) {
+        // the same plane of the neighbour sits at the same offset of ITS arena
+        const int H = L.stripHalo;
+        const size_t offX = (char *)L.x[dst] - (char *)ctx->arena, offP = (char *)L.x[dst + 1] - (char *)ctx->arena;
+        const size_t offW = (char *)L.dStripWords - (char *)ctx->arena;
+        const int gt = L.stripOwnBegin - L.stripBegin;                       // ghost rows above my own rows
+        const int own1 = gt + (L.stripOwnEnd - L.stripOwnBegin);
+        hp.pitch = L.pitchF;
+        hp.storeLo = 0;
+        hp.storeHi = 0x7FFFFFFF;
+        if (ctx->peerUp && L.stripUpWinBegin >= 0) hp.storeLo = gt;       // the rank above fills my upper ghost rows
+        if (ctx->peerDn && L.stripDnWinBegin >= 0) hp.storeHi = own1;     // the rank below fills my lower ghost rows
+        if (ctx->peerUp && L.stripUpWinBegin >= 0) {
+            hp.upX = (float *)(ctx->peerUp + offX); hp.upP = (float *)(ctx->peerUp + offP);
+            hp.upLo = gt; hp.upHi = gt + H;
+            hp.upDelta = L.stripBegin - L.stripUpWinBegin;                   // window-local row -> neighbour's window-local row
+            hp.upFlag = (unsigned int *)(ctx->peerUp + offW) + 2;            // "written by the rank below"
+            hp.waitUp = L.dStripWords + 1;
+        }
+        if (ctx->peerDn && L.stripDnWinBegin >= 0) {
+            hp.dnX = (float *)(ctx->peerDn + offX); hp.dnP = (float *)(ctx->peerDn + offP);
+            hp.dnLo = own1 - H; hp.dnHi = own1;
+            hp.dnDelta = L.stripBegin - L.stripDnWinBegin;
+            hp.dnFlag = (unsigned int *)(ctx->peerDn + offW) + 1;            // "written by the rank above"
+            hp.waitDn = L.dStripWords + 2;
+        }
+        hp.counter = L.dStripWords;
+        hp.doneTarget = L.stripCtaAbs;                                       // the launcher adds this pass's CTA count
+        hp.flagValue = L.stripPassAbs + 1;
+        hp.waitValue = (L.stripPassAbs > L.stripFirstPassAbs) ? L.stripPassAbs : 0;   // first pass of a level: nothing to wait for
+    }
     RTDD_TRY(rtdd::launch_sweep_blocked(ctx->stream, W, ctx->dLut, L.x[src], L.x[src + 1], L.x[dst], L.x[dst + 1], pack, haloT, nsweeps, 0.99f,
-                                        firstSweep == 0, ctx->smCount, &tgt), "rtdd_strip_pass");
+                                        firstSweep == 0, ctx->smCount, &tgt, fused ? &hp : nullptr), "rtdd_strip_pass");
+    if (fused) { L.stripCtaAbs = hp.doneTarget; L.stripPassAbs++; }
     ctx->launches++;
     L.stripPair = dst;
     return 0;

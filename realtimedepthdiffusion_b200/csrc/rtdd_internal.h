@@ -33,6 +33,11 @@ struct RtddLevel {
     int lastIters = 0, lastKernels = 0;
     // row-strip mode (rtdd_strip_*): the level's planes hold rows [stripBegin, stripBegin + stripRows) of the level
     int stripBegin = 0, stripRows = 0, stripPair = 0;
+    // fused halo push (rtdd_strip_neighbours): geometry of this rank's strip and of its neighbours' windows
+    bool stripFused = false;
+    int stripOwnBegin = 0, stripOwnEnd = 0, stripHalo = 0, stripUpWinBegin = -1, stripDnWinBegin = -1;
+    unsigned int stripPassAbs = 0, stripFirstPassAbs = 0, stripCtaAbs = 0;   // monotonically increasing tickets
+    unsigned int *dStripWords = nullptr;   // [0] CTA ticket, [1] flag written by the rank above, [2] flag written by the rank below
     unsigned int *dResidual = nullptr;   // bits of the max-norm of the last sweep's update (rtdd_level_residual)
 };
 
@@ -78,6 +83,7 @@ struct rtdd_ctx {
     float hLut[257];
     bool lutLoaded = false;
     int variant = 0;             // 0 auto, 1 single-sweep, 2 temporally blocked, 3 cluster-resident
+    char *peerUp = nullptr, *peerDn = nullptr;   // neighbours' arenas (IPC-mapped or same-process), same layout as `arena`
     float *dOmega = nullptr;     // the omega schedule (prefix-stable), dOmegaCap entries
     int dOmegaCap = 0;
     int sweepsPerPass = 0;       // 0 auto
@@ -111,6 +117,21 @@ struct SweepTarget {
     uint8_t *u8; int pitchU8;    // may be null
     unsigned int *res;           // may be null: receives the bits of max |x_K - x_{K-1}| (atomicMax)
 };
+// fused multi-GPU halo push (solver_kernels.cu); plain data, filled by rtdd_strip_pass
+struct HaloPush {
+    float *upX, *upP, *dnX, *dnP;          // neighbour's (x_{k+1}, x_k) planes, window-local row 0; null = no such neighbour
+    int upLo, upHi, upDelta;               // my window rows [upLo, upHi) land in neighbour row (row + upDelta)
+    int dnLo, dnHi, dnDelta;
+    int pitch;                             // floats per row (identical on every rank)
+    int storeLo, storeHi;                  // only window rows [storeLo, storeHi) are stored locally: ghost rows that a neighbour
+                                           // fills must not be overwritten with this rank's stale values
+    unsigned int *counter;                 // this rank's CTA completion ticket (null = fused mode off)
+    unsigned int doneTarget;               // ticket value once every CTA of this pass has finished
+    unsigned int *upFlag, *dnFlag;         // flags in the neighbours' memory, set to flagValue by the last CTA
+    unsigned int flagValue;
+    const unsigned int *waitUp, *waitDn;   // this rank's flags: spin until >= waitValue before touching ghost rows (0 = no wait)
+    unsigned int waitValue;
+};
 cudaError_t launch_level_init(cudaStream_t s, const RtddLevel &L, const float *depth, size_t depthPitch,
                               const uint8_t *scribble, size_t scribblePitch,
                               const uint8_t *gray, size_t grayPitch, bool coarsest, int threshold, float *x0);
@@ -121,7 +142,8 @@ cudaError_t launch_sweep_single(cudaStream_t s, const RtddLevel &L, const float 
 struct OmegaPack { float w[RTDD_MAX_T]; };
 cudaError_t launch_sweep_blocked(cudaStream_t s, const RtddLevel &L, const float *lut, const float *x, const float *prev,
                                  float *xOut, float *prevOut, OmegaPack om, int T, int nsweeps, float gamma, bool firstSweep, int smCount,
-                                 const SweepTarget *target = nullptr);
+                                 const SweepTarget *target = nullptr, struct HaloPush *push = nullptr);
+cudaError_t launch_halo_wait(cudaStream_t s, const unsigned int *waitUp, const unsigned int *waitDn, unsigned int value);
 int blocked_max_T();
 void set_blocked_tile_override(int tile);
 void set_blocked_tma(int enabled);

@@ -84,12 +84,22 @@ def frame_coroutine(engine, rank, nranks, max_iterations, halo=8, min_strip_pixe
             a, b = plan[l][rank]
             w0, w1 = max(0, a - halo), min(rows, b + halo)
             engine.strip_init(l, w0, w1)
+            fused = bool(getattr(engine, "fused_halo", False))
+            if fused:
+                # the sweep passes push their boundary rows into the neighbours' ghost rows themselves (peer memory)
+                up0 = max(0, plan[l][rank - 1][0] - halo) if rank > 0 else -1
+                dn0 = max(0, plan[l][rank + 1][0] - halo) if rank < nranks - 1 else -1
+                engine.strip_neighbours(l, a, b, halo, up0, dn0)
             k = 0
             while k < iters:
                 n = min(halo, iters - k)
                 engine.strip_pass(l, k, n, halo)
                 k += n
-                if k < iters or l > 0:                            # the last exchange feeds the prolongation
+                if fused:
+                    if k >= iters and l > 0:
+                        engine.strip_wait(l)                      # ghost rows must be final before the prolongation reads them
+                    yield Exchange(l, None, None, None, None)     # no data: only keeps single-process emulations in lockstep
+                elif k < iters or l > 0:                          # the last exchange feeds the prolongation
                     xk, xkm1 = engine.strip_planes(l)
                     gt, gb = a - w0, w1 - b                       # ghost rows above / below
                     own0, own1 = gt, gt + (b - a)
@@ -146,6 +156,13 @@ def run_distributed(engine, dist, max_iterations, halo=8, min_strip_pixels=1 << 
     except StopIteration as done:
         plan, own = done.value
     return plan, own, exchanges
+
+
+def enable_fused_halo_local(engines):
+    """Single-process emulation: the neighbours' arenas are ordinary device pointers of the same process."""
+    bases = [e.arena()[0] for e in engines]
+    for r, e in enumerate(engines):
+        e.set_peers(bases[r - 1] if r > 0 else None, bases[r + 1] if r + 1 < len(engines) else None)
 
 
 def run_local(engines, max_iterations, halo=8, min_strip_pixels=1 << 22):
@@ -205,6 +222,7 @@ class GpuStripEngine:
         self.depth = [pitched_empty(r, c, torch.float32, self.dev, fill=255.0) for r, c in self.sizes]
         self.depth_u8 = pitched_empty(rows, cols, torch.uint8, self.dev, fill=0)
         self._views = {}
+        self.fused_halo = False      # set by set_peers / enable_fused_halo_distributed
         self.marks = None            # set to [] to collect (label, event) pairs for one frame
 
     # -- helpers ------------------------------------------------------------------
@@ -275,6 +293,42 @@ class GpuStripEngine:
                 self._views[key] = torch.as_tensor(h, device=self.dev)
             out.append(self._views[key])
         return out
+
+    # -- fused halo push (peer memory) -----------------------------------------------------------
+    def arena(self):
+        from ._native import lib
+        base, nbytes = C.c_void_p(), C.c_size_t()
+        self._ck(lib.rtdd_arena(self.ctx._h, C.byref(base), C.byref(nbytes)))
+        return base.value, nbytes.value
+
+    def set_peers(self, above, below):
+        from ._native import lib
+        self._ck(lib.rtdd_strip_set_peers(self.ctx._h, C.c_void_p(above or 0), C.c_void_p(below or 0)))
+        self.fused_halo = bool(above or below)
+
+    def enable_fused_halo_distributed(self, dist):
+        """Exchange CUDA IPC handles of the arenas with the two neighbouring ranks and map them."""
+        from ._native import lib
+        rank, world = dist.get_rank(), dist.get_world_size()
+        h = C.create_string_buffer(64)
+        self._ck(lib.rtdd_ipc_export(self.ctx._h, h))
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(h.raw))
+        ptrs = {}
+        for nb in (rank - 1, rank + 1):
+            if 0 <= nb < world:
+                p = C.c_void_p()
+                self._ck(lib.rtdd_ipc_import(self.ctx._h, C.create_string_buffer(handles[nb], 64), C.byref(p)))
+                ptrs[nb] = p.value
+        self.set_peers(ptrs.get(rank - 1), ptrs.get(rank + 1))
+
+    def strip_neighbours(self, l, a, b, halo, up0, dn0):
+        from ._native import lib
+        self._ck(lib.rtdd_strip_neighbours(self.ctx._h, l, int(a), int(b), int(halo), int(up0), int(dn0)))
+
+    def strip_wait(self, l):
+        from ._native import lib
+        self._ck(lib.rtdd_strip_wait(self.ctx._h, l))
 
     def strip_finish(self, l, r0, r1):
         from ._native import lib

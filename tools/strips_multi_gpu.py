@@ -78,6 +78,7 @@ def main():
     ap.add_argument("--halo", type=int, default=8)
     ap.add_argument("--min-strip-pixels", type=int, default=1 << 22)
     ap.add_argument("--check", action="store_true")
+    ap.add_argument("--fused", action="store_true", help="halo rows pushed by the sweep kernels over peer memory instead of NCCL send/recv")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -92,6 +93,8 @@ def main():
     with torch.cuda.stream(stream):
         bgr, scribble, edited = synth_on_device(rows, cols, 1005, ctx)
         eng = strips.GpuStripEngine(ctx, bgr, scribble, edited)
+        if args.fused and world > 1:
+            eng.enable_fused_halo_distributed(dist)
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
         def frame():
@@ -146,8 +149,8 @@ def main():
             it = strips.level_iterations(1000, L, l)
             total += r * c * it
             per.append({"level": l, "size": "%dx%d" % (c, r), "sweeps": it, "split": plan[l] is not None})
-        print(json.dumps({"workload": "configs[4]: %dx%d single synthetic image, row strips + NVLink halo exchange (NCCL send/recv), halo %d rows"
-                                      % (cols, rows, args.halo),
+        print(json.dumps({"workload": "configs[4]: %dx%d single synthetic image, row strips + NVLink halo exchange (%s), halo %d rows%s"
+                                      % (cols, rows, "peer-memory stores + flags" if args.fused else "NCCL send/recv", args.halo, ", FUSED: halo rows pushed by the sweep kernels over peer memory" if args.fused else ""),
                           "n_gpus": world, "ms_per_solve": float(t.item()), "Mpixel-sweeps/s": total / (float(t.item()) * 1e-3) / 1e6,
                           "pixel_sweeps": total, "halo_exchanges_per_solve": exchanges, "levels": per, "scaling": "strong",
                           "bit_identical_to_single_gpu": ok, "rank0_phase_ms": [[k, round(v, 4)] for k, v in phases]}), flush=True)
