@@ -155,6 +155,9 @@ int rtdd_arena(rtdd_ctx *ctx, void **base, size_t *bytes);
 int rtdd_strip_set_peers(rtdd_ctx *ctx, void *arenaAbove, void *arenaBelow);
 int rtdd_strip_neighbours(rtdd_ctx *ctx, int level, int ownBegin, int ownEnd, int halo, int aboveWinBegin, int belowWinBegin);
 int rtdd_strip_wait(rtdd_ctx *ctx, int level);
+/* on = 0: the following passes of `level` keep their boundary rows to themselves (the finest level's last pass: nobody
+ * reads the ghost rows afterwards); the flags are still raised.  Reset to on by rtdd_strip_neighbours. */
+int rtdd_strip_push_enable(rtdd_ctx *ctx, int level, int on);
 /* cv::pyrUp restricted to destination rows [rowBegin, rowEnd); src and dst are the full planes */
 int rtdd_pyrup_depth_rows(rtdd_ctx *ctx, const float *src, size_t srcPitch, int srcRows, int srcCols,
                           float *dst, size_t dstPitch, int dstRows, int dstCols, int rowBegin, int rowEnd);

@@ -670,6 +670,15 @@ int rtdd_strip_neighbours(rtdd_ctx *ctx, int level, int ownBegin, int ownEnd, in
     L.stripOwnBegin = ownBegin; L.stripOwnEnd = ownEnd; L.stripHalo = halo;
     L.stripUpWinBegin = aboveWinBegin; L.stripDnWinBegin = belowWinBegin;
     L.stripFused = true;
+    L.stripPushOff = false;
+    return 0;
+}
+
+int rtdd_strip_push_enable(rtdd_ctx *ctx, int level, int on)
+{
+    if (!ctx) return RTDD_E_ARG;
+    if (level < 0 || level >= ctx->levels) return rtdd_fail(ctx, RTDD_E_ARG, "rtdd_strip_push_enable");
+    ctx->lv[level].stripPushOff = !on;
     return 0;
 }
 
@@ -719,14 +728,14 @@ int rtdd_strip_pass(rtdd_ctx *ctx, int level, int firstSweep, int nsweeps, int h
         hp.storeHi = 0x7FFFFFFF;
         if (ctx->peerUp && L.stripUpWinBegin >= 0) hp.storeLo = gt;       // the rank above fills my upper ghost rows
         if (ctx->peerDn && L.stripDnWinBegin >= 0) hp.storeHi = own1;     // the rank below fills my lower ghost rows
-        if (ctx->peerUp && L.stripUpWinBegin >= 0) {
+        if (ctx->peerUp && L.stripUpWinBegin >= 0 && !L.stripPushOff) {
             hp.upX = (float *)(ctx->peerUp + offX); hp.upP = (float *)(ctx->peerUp + offP);
             hp.upLo = gt; hp.upHi = gt + H;
             hp.upDelta = L.stripBegin - L.stripUpWinBegin;                   // window-local row -> neighbour's window-local row
             hp.upFlag = (unsigned int *)(ctx->peerUp + offW) + 2;            // "written by the rank below"
             hp.waitUp = L.dStripWords + 1;
         }
-        if (ctx->peerDn && L.stripDnWinBegin >= 0) {
+        if (ctx->peerDn && L.stripDnWinBegin >= 0 && !L.stripPushOff) {
             hp.dnX = (float *)(ctx->peerDn + offX); hp.dnP = (float *)(ctx->peerDn + offP);
             hp.dnLo = own1 - H; hp.dnHi = own1;
             hp.dnDelta = L.stripBegin - L.stripDnWinBegin;

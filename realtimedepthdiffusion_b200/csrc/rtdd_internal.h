@@ -34,7 +34,7 @@ struct RtddLevel {
     // row-strip mode (rtdd_strip_*): the level's planes hold rows [stripBegin, stripBegin + stripRows) of the level
     int stripBegin = 0, stripRows = 0, stripPair = 0;
     // fused halo push (rtdd_strip_neighbours): geometry of this rank's strip and of its neighbours' windows
-    bool stripFused = false;
+    bool stripFused = false, stripPushOff = false;
     int stripOwnBegin = 0, stripOwnEnd = 0, stripHalo = 0, stripUpWinBegin = -1, stripDnWinBegin = -1;
     unsigned int stripPassAbs = 0, stripFirstPassAbs = 0, stripCtaAbs = 0;   // monotonically increasing tickets
     unsigned int *dStripWords = nullptr;   // [0] CTA ticket, [1] flag written by the rank above, [2] flag written by the rank below

@@ -93,6 +93,8 @@ def frame_coroutine(engine, rank, nranks, max_iterations, halo=8, min_strip_pixe
             k = 0
             while k < iters:
                 n = min(halo, iters - k)
+                if fused and l == 0 and k + n >= iters:
+                    engine.strip_push_enable(l, False)            # the finest level's last pass: nobody reads the ghost rows afterwards
                 engine.strip_pass(l, k, n, halo)
                 k += n
                 if fused:
@@ -329,6 +331,10 @@ class GpuStripEngine:
     def strip_wait(self, l):
         from ._native import lib
         self._ck(lib.rtdd_strip_wait(self.ctx._h, l))
+
+    def strip_push_enable(self, l, on):
+        from ._native import lib
+        self._ck(lib.rtdd_strip_push_enable(self.ctx._h, l, 1 if on else 0))
 
     def strip_finish(self, l, r0, r1):
         from ._native import lib
