@@ -715,7 +715,13 @@ int rtdd_strip_pass(rtdd_ctx *ctx, int level, int firstSweep, int nsweeps, int h
     const rtdd::SweepTarget tgt = {nullptr, 0, nullptr, 0, L.dResidual};
     RTDD_TRY(cudaMemsetAsync(L.dResidual, 0, sizeof(unsigned int), ctx->stream), "rtdd_strip_pass");
     rtdd::HaloPush hp = {};
-    const bool fused = L.stripFused && (ctx->peerUp || ctx->peerDn);
+    bool fused = L.stripFused && (ctx->peerUp || ctx->peerDn);
+    // a pass that neither waits for nor feeds a neighbour (the finest level's only pass) runs the plain kernel
+    const bool firstOfLevel = (L.stripPassAbs == L.stripFirstPassAbs);
+    if (fused && L.stripPushOff && firstOfLevel) {
+        fused = false;
+        L.stripPassAbs++;               // keep the pass tickets of all ranks in step
+    }
     if (fused) {
         // the same plane of the neighbour sits at the same offset of ITS arena
         const int H = L.stripHalo;
