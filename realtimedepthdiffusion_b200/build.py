@@ -63,7 +63,7 @@ def build_rtdd(force=False, verbose=False, extra=()):
     os.makedirs(LIBDIR, exist_ok=True)
     cmd = [_nvcc()] + ARCH + ["-O3", "-lineinfo", "-std=c++17", "-shared", "-Xcompiler", "-fPIC",
                               "-Xlinker", "-Bsymbolic", "-x", "cu",
-                              "-I", os.path.join(ROOT, "include"), "-I", CSRC] + list(extra) + srcs + ["-o", LIBRTDD]
+                              "-I", os.path.join(ROOT, "include"), "-I", CSRC] + list(extra) + os.environ.get("RTDD_EXTRA_NVCC", "").split() + srcs + ["-o", LIBRTDD]
     _run(cmd, verbose)
     return LIBRTDD
 
