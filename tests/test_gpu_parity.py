@@ -617,3 +617,20 @@ def test_independent_contexts_on_concurrent_streams(rtdd):
         ref.close()
         ctx.close()
     assert len(want) == 3
+
+
+def test_contexts_on_two_gpus_in_one_process(rtdd):
+    """One context per GPU in ONE process (the C ABI's explicit handle): both devices give the oracle's bits."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    rows, cols, iters = 300, 700, 120
+    bgr, scribble, edited = synth.synth_case(rows, cols, 31)
+    want = ob.FrameState(bgr)
+    want.solve(scribble, edited, iters)
+    for dev in (1, 0, 1):
+        ctx = rtdd.DepthDiffusion(rows, cols, device=dev)
+        ctx.frame_set_image(bgr)
+        ctx.frame_solve_host(scribble, edited, iters, np.zeros((rows, cols), np.uint8))
+        got = ctx.frame_plane(ctx.PLANE_DEPTH, 0).cpu().numpy()
+        assert np.array_equal(got.view(np.uint32), want.depth[0].view(np.uint32)), dev
+        ctx.close()
