@@ -444,6 +444,13 @@ int rtdd_set_tuning(rtdd_ctx *ctx, const char *key, int value)
         destroy_graphs(ctx);
         return 0;
     }
+    if (strcmp(key, "pdl") == 0 && (value == 0 || value == 1)) {
+        rtdd::set_pdl(value);
+        DeviceGuard guard(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+        destroy_graphs(ctx);
+        return 0;
+    }
     if (strcmp(key, "blocked_tma") == 0 && (value == 0 || value == 1)) {
         rtdd::set_blocked_tma(value);
         DeviceGuard guard(ctx->device);

@@ -148,6 +148,7 @@ int blocked_max_T();
 void set_blocked_tile_override(int tile);
 void set_blocked_tma(int enabled);
 void set_resident_warps(int w);
+void set_pdl(int on);
 void set_resident_two_sweep(int on);
 // resident (one cluster, all sweeps in one launch); omegas = device array of nsweeps floats
 bool resident_plan(int rows, int cols, int *R, int *clusterSize, int *blocksPerCta, int *WX);
