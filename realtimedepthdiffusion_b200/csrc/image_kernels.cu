@@ -30,6 +30,8 @@ __global__ void __launch_bounds__(256)
 convert4_kernel(const uint8_t *__restrict__ src, size_t srcPitch, float *__restrict__ dst, size_t dstPitch,
                 const uint8_t *__restrict__ mask, size_t maskPitch, int rows, int cols)
 {
+    asm volatile("griddepcontrol.wait;" ::: "memory");               // programmatic dependent launch: predecessor complete
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x4 >= cols || y >= rows) return;
@@ -53,8 +55,7 @@ cudaError_t launch_convert(cudaStream_t s, const uint8_t *src, size_t srcPitch, 
     if ((((uintptr_t)mask | maskPitch) & 3u) == 0) {
         dim3 block(64, 4);
         dim3 grid(rtdd_div_up(rtdd_div_up(cols, 4), block.x), rtdd_div_up(rows, block.y));
-        convert4_kernel<<<grid, block, 0, s>>>(src, srcPitch, dst, dstPitch, mask, maskPitch, rows, cols);
-        return cudaGetLastError();
+        return launch_pdl(convert4_kernel, grid, block, (size_t)0, s, src, srcPitch, dst, dstPitch, mask, maskPitch, rows, cols);
     }
     dim3 block(64, 4);
     dim3 grid(rtdd_div_up(cols, block.x), rtdd_div_up(rows, block.y));
@@ -104,6 +105,8 @@ pyrdown_annotation4_kernel(const uint8_t *__restrict__ prevScribble, size_t prev
                            uint8_t *__restrict__ currScribble, size_t currScribblePitch,
                            uint8_t *__restrict__ currEdited, size_t currEditedPitch, int currentRows, int currentCols)
 {
+    asm volatile("griddepcontrol.wait;" ::: "memory");               // programmatic dependent launch: predecessor complete
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x4 >= currentCols || y >= currentRows) return;
@@ -170,10 +173,8 @@ cudaError_t launch_pyrdown_annotation(cudaStream_t s, const uint8_t *prevScribbl
     if ((((uintptr_t)prevScribble | prevScribblePitch) & 7u) == 0) {
         dim3 block(64, 4);
         dim3 grid(rtdd_div_up(rtdd_div_up(currentCols, 4), block.x), rtdd_div_up(currentRows, block.y));
-        pyrdown_annotation4_kernel<<<grid, block, 0, s>>>(prevScribble, prevScribblePitch, prevEdited, prevEditedPitch,
-                                                          previousRows, previousCols, currScribble, currScribblePitch,
-                                                          currEdited, currEditedPitch, currentRows, currentCols);
-        return cudaGetLastError();
+        return launch_pdl(pyrdown_annotation4_kernel, grid, block, (size_t)0, s, prevScribble, prevScribblePitch, prevEdited, prevEditedPitch,
+                          previousRows, previousCols, currScribble, currScribblePitch, currEdited, currEditedPitch, currentRows, currentCols);
     }
     dim3 block(64, 4);
     dim3 grid(rtdd_div_up(currentCols, block.x), rtdd_div_up(currentRows, block.y));
@@ -347,6 +348,8 @@ __global__ void __launch_bounds__(256)
 pyrup_depth4_kernel(const float *__restrict__ src, size_t srcPitch, int srows, int scols,
                     float *__restrict__ dst, size_t dstPitch, int drows, int dcols, int rowBegin, int rowEnd)
 {
+    asm volatile("griddepcontrol.wait;" ::: "memory");               // programmatic dependent launch: predecessor complete
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int j = blockIdx.x * blockDim.x + threadIdx.x;            // destination columns 4j..4j+3
     const int y = (rowBegin >> 1) + blockIdx.y * blockDim.y + threadIdx.y;   // source row; destination rows 2y, 2y+1
     const int dx0 = 4 * j;
@@ -412,8 +415,7 @@ cudaError_t launch_pyrup_depth_rows(cudaStream_t s, const float *src, size_t src
         if (y1 > srows - 1) y1 = srows - 1;
         dim3 block(32, 8);
         dim3 grid(rtdd_div_up(rtdd_div_up(dcols, 4), block.x), rtdd_div_up(y1 - y0 + 1, block.y));
-        pyrup_depth4_kernel<<<grid, block, 0, s>>>(src, srcPitch, srows, scols, dst, dstPitch, drows, dcols, rowBegin, rowEnd);
-        return cudaGetLastError();
+        return launch_pdl(pyrup_depth4_kernel, grid, block, (size_t)0, s, src, srcPitch, srows, scols, dst, dstPitch, drows, dcols, rowBegin, rowEnd);
     }
     dim3 block(64, 4);
     dim3 grid(rtdd_div_up(dcols, block.x), rtdd_div_up(rowEnd - rowBegin, block.y));

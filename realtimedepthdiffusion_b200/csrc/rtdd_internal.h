@@ -149,6 +149,26 @@ void set_blocked_tile_override(int tile);
 void set_blocked_tma(int enabled);
 void set_resident_warps(int w);
 void set_pdl(int on);
+int pdl_enabled();
+
+// Programmatic dependent launch (sm_90+): the kernel may be scheduled while its predecessor in the stream drains; it orders
+// itself against the predecessor's memory with griddepcontrol.wait (every kernel launched through here executes it before
+// its first dependent access).  Captured into CUDA graphs as programmatic edges.
+template <class Kernel, class... Args>
+static inline cudaError_t launch_pdl(Kernel kernel, dim3 grid, dim3 block, size_t smemBytes, cudaStream_t s, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smemBytes;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
 void set_resident_two_sweep(int on);
 // resident (one cluster, all sweeps in one launch); omegas = device array of nsweeps floats
 bool resident_plan(int rows, int cols, int *R, int *clusterSize, int *blocksPerCta, int *WX);
