@@ -634,3 +634,48 @@ def test_contexts_on_two_gpus_in_one_process(rtdd):
         got = ctx.frame_plane(ctx.PLANE_DEPTH, 0).cpu().numpy()
         assert np.array_equal(got.view(np.uint32), want.depth[0].view(np.uint32)), dev
         ctx.close()
+
+
+def _misaligned(a, channels=1):
+    """Device copy of `a` whose first byte sits 1 element past a 512-byte boundary and whose pitch is odd-sized:
+    none of the vector paths (float4 / u32 / u64 / TMA-direct output) may be taken."""
+    a = np.ascontiguousarray(a)
+    rows = a.shape[0]
+    flat = torch.from_numpy(a.reshape(rows, -1))
+    width = flat.shape[1]
+    base = torch.zeros((rows, width + 3), dtype=flat.dtype, device="cuda")
+    view = base[:, 1:1 + width]
+    view.copy_(flat)
+    return view
+
+
+def test_misaligned_caller_planes_take_the_scalar_paths(rtdd):
+    rows, cols, iters = 135, 241, 40
+    gray, depth, scribble = random_level(rows, cols, 404)
+    rng = np.random.default_rng(4)
+    edited = rng.integers(0, 256, (rows, cols, 3), dtype=np.uint8)
+    want = ob.solve_level(ob.convert_to_float(edited, depth, scribble), scribble, gray, iters, 0, 0)
+    ctx = rtdd.DepthDiffusion(rows, cols, 1)
+    d, s, g, e = _misaligned(depth), _misaligned(scribble), _misaligned(gray), _misaligned(edited, 3)
+    assert d.data_ptr() % 16 != 0 and s.data_ptr() % 4 != 0
+    ctx.convert_to_float(e, d, s)
+    ctx.matrix_free_solver(d, s, g, iters, 0)
+    ctx.sync()
+    assert np.array_equal(d.cpu().numpy().view(np.uint32), want.view(np.uint32))
+    q = _misaligned(np.zeros((rows, cols), np.uint8))
+    ctx.quantise_u8(d, q)
+    assert np.array_equal(q.cpu().numpy(), ob.quantise_u8(want))
+    cs, ce = _misaligned(np.zeros((rows // 2, cols // 2), np.uint8)), _misaligned(np.zeros((rows // 2, cols // 2, 3), np.uint8), 3)
+    ctx.pyrdown_annotation(s, e, cs, ce)
+    ws, we = ob.pyrdown_annotation(scribble, edited, np.zeros((rows // 2, cols // 2), np.uint8), np.zeros((rows // 2, cols // 2, 3), np.uint8))
+    assert np.array_equal(cs.cpu().numpy(), ws) and np.array_equal(ce.cpu().numpy().reshape(rows // 2, cols // 2, 3), we)
+    up = _misaligned(np.zeros((2 * rows + 1, 2 * cols), np.float32))
+    ctx.pyrup_depth(d, up)
+    assert np.array_equal(up.cpu().numpy().view(np.uint32), ob.pyrup_f32(want, 2 * rows + 1, 2 * cols).view(np.uint32))
+    outs = [_misaligned(np.zeros((rows, cols, 3), np.uint8), 3) for _ in range(3)]
+    ctx.simulate_desaturation(e, g, d, outs[0])
+    ctx.simulate_defocus(e, d, outs[2])
+    ctx.sync()
+    assert np.array_equal(outs[0].cpu().numpy().reshape(rows, cols, 3), ob.desaturate(edited, gray, want))
+    assert np.array_equal(outs[2].cpu().numpy().reshape(rows, cols, 3), ob.defocus(edited, want))
+    ctx.close()
