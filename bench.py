@@ -120,14 +120,6 @@ def max_over_ranks(dist, v):
     return float(t.item())
 
 
-def sum_over_ranks(dist, v):
-    if dist is None:
-        return v
-    t = torch.tensor([v], dtype=torch.float64, device="cuda")
-    dist.all_reduce(t, op=dist.ReduceOp.SUM)
-    return float(t.item())
-
-
 def pixel_sweeps(rows, cols, levels, max_iterations=1000):
     from realtimedepthdiffusion_b200 import level_iterations, level_sizes
     total, per = 0, []

@@ -7,7 +7,6 @@ meaning, device planes with byte pitches; errors raise RtddError instead of the
 reference's print-and-continue (the C++ shims keep that convention).
 """
 import ctypes as C
-import math
 
 import torch
 

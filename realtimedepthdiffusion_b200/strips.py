@@ -16,7 +16,6 @@ The engine behind it is duck-typed: `GpuStripEngine` (this file) calls librtdd.s
 the CPU tests plug in an oracle-backed engine to check the decomposition logic itself.
 """
 import ctypes as C
-import math
 
 import torch
 
