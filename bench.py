@@ -139,6 +139,10 @@ def cpu_baseline(rows, cols, levels, budget_s=12.0):
     depth = np.full((rows, cols), 255.0, np.float32)
     depth = ob.convert_to_float(edited, depth, scribble)
     lut = ob.load_weights(0.4)
+    try:
+        ob.set_num_threads(len(os.sched_getaffinity(0)))       # torchrun exports OMP_NUM_THREADS=1: use every core we may run on
+    except AttributeError:
+        ob.set_num_threads(os.cpu_count() or 1)
     iters = level_iterations(1000, levels, 0)
     ob.solve_level(depth[:64], scribble[:64], gray[:64], 2, 0, levels - 1, lut)     # warm the OpenMP pool
     t0 = time.perf_counter()
