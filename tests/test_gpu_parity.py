@@ -679,3 +679,28 @@ def test_misaligned_caller_planes_take_the_scalar_paths(rtdd):
     assert np.array_equal(outs[0].cpu().numpy().reshape(rows, cols, 3), ob.desaturate(edited, gray, want))
     assert np.array_equal(outs[2].cpu().numpy().reshape(rows, cols, 3), ob.defocus(edited, want))
     ctx.close()
+
+
+@pytest.mark.parametrize("name", ["dog", "womanparasol"])
+def test_whole_frame_entry_point_on_dataset_pairs(rtdd, name):
+    """BASELINE configs[0] through rtdd_frame_*: dataset image + annotation, native resolution, the reference's 1000-sweep
+    schedule; the u8 map must equal the golden recorded from the reference's kernels, the fp32 map the oracle's bits."""
+    from tests.test_oracle_cpu import _load_case
+    z = np.load(os.path.join(GOLD, "ref_solver_%s.npz" % name))
+    bgr, scribble, edited = _load_case(name)
+    rows, cols = scribble.shape
+    ctx = rtdd.DepthDiffusion(rows, cols)
+    assert ctx.levels == int(z["levels"])
+    ctx.frame_set_image(bgr)
+    u8 = ctx.frame_solve_host(scribble, edited, 1000, np.zeros((rows, cols), np.uint8)).numpy()
+    assert np.array_equal(u8, z["depth_u8"])
+    assert sha(ctx.frame_plane(ctx.PLANE_DEPTH, 0).cpu().numpy()) == str(z["out_sha_0"])
+    for l in range(1, ctx.levels):
+        assert sha(ctx.frame_plane(ctx.PLANE_DEPTH, l).cpu().numpy()) == str(z["out_sha_%d" % l]), l
+    # second frame with one more stroke (state carried over exactly like main.cpp)
+    ev = synth.brush_events(rows, cols, 99, 1, 6)
+    s2, e2 = synth.paint_events(bgr, ev, scribble.copy(), edited.copy())
+    u8b = ctx.frame_solve_host(s2, e2, 1000, np.zeros((rows, cols), np.uint8)).numpy()
+    assert np.array_equal(u8b, z["frame2_depth_u8"])
+    assert sha(ctx.frame_plane(ctx.PLANE_DEPTH, 0).cpu().numpy()) == str(z["frame2_out_sha_0"])
+    ctx.close()
