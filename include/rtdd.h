@@ -112,7 +112,8 @@ int rtdd_solve_level_converge(rtdd_ctx *ctx, float *depth, size_t depthPitch, co
  * compiler's IEEE div.rn (the operation the reference's `sum / count` compiles to, ref: src/GPUSolver.cu:104)
  * on n counter-generated operand pairs.  mode 0 = the whole admitted range, 1 = the sweep's typical range,
  * 2 = quotients placed next to rounding boundaries, 3 = tiny/denormal denominators through the exact power-of-two
- * rescaling the resident kernel uses.  *mismatches (HOST) must come back 0. */
+ * rescaling the resident kernel uses, 4 = numerators below 2^-100 (denormals included) through the resident kernel's
+ * exact small-quotient path (div_tiny).  *mismatches (HOST) must come back 0. */
 int rtdd_selftest_division(rtdd_ctx *ctx, unsigned long long n, unsigned long long seed, int mode, unsigned long long *mismatches);
 
 /* Sweep implementation selector for rtdd_solve_level: 0 = auto (default),

@@ -111,7 +111,10 @@ void pick_variant(const rtdd_ctx *ctx, const RtddLevel &L, int iters, int *varia
     int rR, rC, rB, rW;
     const bool fits = rtdd::resident_plan(L.rows, L.cols, &rR, &rC, &rB, &rW);
     if (v == 3 && !fits) v = 2;          // level too large for one cluster: temporally blocked instead
-    if (v == 0) v = (fits && iters >= 8) ? 3 : 2;
+    // measured (tools/coarse_level_cases.py): 240x135 resident 0.23 ms vs blocked 0.36; 256x256 resident 0.30..0.33 (32 warps per
+    // CTA, the 64-register build; two rows per warp no better) vs blocked 0.23..0.26 -- the crossover lies in between
+    const bool residentPays = fits && (long)L.rows * L.cols <= 49152;
+    if (v == 0) v = (residentPays && iters >= 8) ? 3 : 2;
     if (v == 3) {
         t = 0;
     } else if (v == 2) {
@@ -437,6 +440,13 @@ int rtdd_set_tuning(rtdd_ctx *ctx, const char *key, int value)
         destroy_graphs(ctx);
         return 0;
     }
+    if (strcmp(key, "resident_r1_max_warps") == 0 && value >= 1 && value <= 32) {
+        rtdd::set_resident_r1_max_warps(value);
+        DeviceGuard guard(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+        destroy_graphs(ctx);
+        return 0;
+    }
     if (strcmp(key, "resident_two_sweep") == 0 && (value == 0 || value == 1)) {
         rtdd::set_resident_two_sweep(value);
         DeviceGuard guard(ctx->device);
@@ -511,7 +521,7 @@ int rtdd_solve_level(rtdd_ctx *ctx, float *depth, size_t depthPitch, const uint8
 int rtdd_selftest_division(rtdd_ctx *ctx, unsigned long long n, unsigned long long seed, int mode, unsigned long long *mismatches)
 {
     if (!ctx) return RTDD_E_ARG;
-    if (!mismatches || mode < 0 || mode > 3) return rtdd_fail(ctx, RTDD_E_ARG, "rtdd_selftest_division");
+    if (!mismatches || mode < 0 || mode > 4) return rtdd_fail(ctx, RTDD_E_ARG, "rtdd_selftest_division");
     DeviceGuard guard(ctx->device);
     unsigned long long *d = nullptr;
     RTDD_TRY(cudaMalloc((void **)&d, sizeof(*d)), "rtdd_selftest_division");

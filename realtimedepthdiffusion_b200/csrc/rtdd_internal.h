@@ -148,6 +148,7 @@ int blocked_max_T();
 void set_blocked_tile_override(int tile);
 void set_blocked_tma(int enabled);
 void set_resident_warps(int w);
+void set_resident_r1_max_warps(int w);
 void set_pdl(int on);
 int pdl_enabled();
 

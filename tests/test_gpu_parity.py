@@ -176,7 +176,7 @@ def test_edge_weight_pass_vs_oracle(rtdd, rows, cols, level, levels):
 
 def test_branch_free_division_matches_ieee_division(rtdd):
     ctx = rtdd.DepthDiffusion(8, 8, 1)
-    for mode in (0, 1, 2, 3):
+    for mode in (0, 1, 2, 3, 4):
         assert ctx.selftest_division(1 << 31, seed=12345 + mode, mode=mode) == 0, mode
     ctx.close()
 
@@ -219,6 +219,47 @@ def test_salt_and_pepper_image_tiny_weight_sums(rtdd, rows, cols, level, levels)
         ctx.set_sweep_variant(variant, T)
         d, s, g = to_dev(depth), to_dev(scribble), to_dev(gray)
         ctx.matrix_free_solver(d, s, g, 40, level)
+        ctx.sync()
+        assert np.array_equal(to_host(d).view(np.uint32), want.view(np.uint32)), (variant, T)
+        ctx.close()
+
+
+def enclosed_zero_level(rows, cols, seed):
+    """Free pockets (1x1 ... 5x5) enclosed by depth-0 scribbles next to an ordinary half: the pockets decay geometrically
+    to zero, pass through numerators below 2^-100 and some end in a +-1..2 ulp denormal limit cycle."""
+    rng = np.random.default_rng(seed)
+    gray = np.full((rows, cols), 100, np.uint8)
+    gray[:, cols // 2:] = rng.integers(90, 110, (rows, cols - cols // 2))
+    scribble = np.zeros((rows, cols), np.uint8)
+    depth = np.full((rows, cols), 255.0, np.float32)
+    half = cols // 2
+    scribble[:, :half] = 255
+    depth[:, :half] = 0.0
+    for _ in range(max(6, rows * half // 60)):
+        h, w = rng.integers(1, 6), rng.integers(1, 6)
+        y, x = rng.integers(1, max(2, rows - h - 1)), rng.integers(1, max(2, half - w - 1))
+        scribble[y:y + h, x:x + w] = 0
+        depth[y:y + h, x:x + w] = 255.0
+    sc = rng.random((rows, cols - half)) < 0.05
+    scribble[:, half:][sc] = 255
+    depth[:, half:][sc] = rng.choice(np.array([0, 64, 128, 192, 254], np.float32), int(sc.sum()))
+    return gray, depth, scribble
+
+
+@pytest.mark.parametrize("rows,cols,iters", [(64, 64, 1000), (67, 120, 1000), (135, 240, 500), (600, 100, 300)])
+def test_pockets_decaying_to_denormals_small_quotient_path(rtdd, rows, cols, iters):
+    """Numerators below 2^-100 for hundreds of sweeps (ref: src/GPUSolver.cu:104 `sum / count` is IEEE div.rn there):
+    the resident kernel's exact small-quotient path (div_tiny) and the blocked kernels' IEEE fallback vs the oracle."""
+    gray, depth, scribble = enclosed_zero_level(rows, cols, rows + cols)
+    want = ob.solve_level(depth, scribble, gray, iters, 0, 0)
+    free = scribble != 255
+    tiny = free & (np.abs(want) < 2.0 ** -100)
+    assert tiny.any(), "the case must reach the tiny range"
+    for variant, T in ((3, 0), (2, 8), (0, 0)):
+        ctx = rtdd.DepthDiffusion(rows, cols, 1)
+        ctx.set_sweep_variant(variant, T)
+        d, s, g = to_dev(depth), to_dev(scribble), to_dev(gray)
+        ctx.matrix_free_solver(d, s, g, iters, 0)
         ctx.sync()
         assert np.array_equal(to_host(d).view(np.uint32), want.view(np.uint32)), (variant, T)
         ctx.close()

@@ -55,6 +55,27 @@ def test_lockstep_strips_are_bit_identical_to_the_single_solve(rows, cols, nrank
     assert np.array_equal(got, want)
 
 
+@pytest.mark.parametrize("rows,cols,nranks,halo,sweeps", [(203, 150, 2, 4, 19), (256, 96, 4, 8, 64), (181, 130, 3, 5, 3)])
+def test_level0_only_strips_match_the_single_level_solve(rows, cols, nranks, halo, sweeps):
+    """configs[4] measurement (i): a fixed number of finest-level sweeps, strip-decomposed, from the same guess."""
+    bgr, scribble, edited = synth.synth_case(rows, cols, 99)
+    rng = np.random.default_rng(5)
+    guess = rng.uniform(0, 255, (rows, cols)).astype(np.float32)
+    solo = CpuStripEngine(bgr, scribble, edited)
+    solo.st.depth[0] = guess.copy()
+    (res, ex0) = strips.run_local([solo], 0, halo=halo, level0_sweeps=sweeps)
+    assert ex0 == 0 and res[0][1] == (0, rows)
+    engines = [CpuStripEngine(bgr, scribble, edited) for _ in range(nranks)]
+    for e in engines:
+        e.st.depth[0] = guess.copy()
+    results, exchanges = strips.run_local(engines, 0, halo=halo, level0_sweeps=sweeps)
+    assert exchanges == (sweeps - 1) // halo                  # one per pass except after the last
+    got = np.zeros((rows, cols), np.float32)
+    for r, (plan, own) in enumerate(results):
+        got[own[0]:own[1]] = engines[r].st.depth[0][own[0]:own[1]]
+    assert np.array_equal(got.view(np.uint32), solo.st.depth[0].view(np.uint32))
+
+
 WORKER = r'''
 import os, sys
 sys.path.insert(0, %(root)r)

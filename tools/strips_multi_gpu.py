@@ -79,6 +79,8 @@ def main():
     ap.add_argument("--min-strip-pixels", type=int, default=1 << 22)
     ap.add_argument("--check", action="store_true")
     ap.add_argument("--fused", action="store_true", help="halo rows pushed by the sweep kernels over peer memory instead of NCCL send/recv")
+    ap.add_argument("--level0-sweeps", type=int, default=0,
+                    help="SURVEY.md 8d config 5 (i): time only this many finest-level sweeps (strip-decomposed) instead of the whole pyramid")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -96,18 +98,38 @@ def main():
         if args.fused and world > 1:
             eng.enable_fused_halo_distributed(dist)
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = args.level0_sweeps
+        guess = None
+        if l0 > 0:
+            # the guess the finest level really starts from: one untimed whole-pyramid frame up to the prolongation
+            if world > 1:
+                strips.run_distributed(eng, dist, 1000, halo=args.halo, min_strip_pixels=args.min_strip_pixels)
+            else:
+                strips.run_local([eng], 1000, halo=args.halo, min_strip_pixels=args.min_strip_pixels)
+            if world > 1:                                        # every rank needs all rows of the guess: take rank order
+                rows0 = eng.depth[0].shape[0]
+                b = [(r * rows0) // world for r in range(world)] + [rows0]
+                for r in range(world):
+                    part = eng.depth[0][b[r]:b[r + 1]]
+                    buf = part.contiguous()
+                    dist.broadcast(buf, src=r)
+                    part.copy_(buf)
+            guess = eng.depth[0].clone()
 
         def frame():
-            for d in eng.depth:
-                d.fill_(255.0)                                   # first-frame state (main.cpp:136), outside the timed region
+            if l0 > 0:
+                eng.depth[0].copy_(guess)                        # outside the timed region
+            else:
+                for d in eng.depth:
+                    d.fill_(255.0)                               # first-frame state (main.cpp:136), outside the timed region
             torch.cuda.synchronize()
             if world > 1:
                 dist.barrier()
             ev0.record(stream)
             if world > 1:
-                plan, own, exchanges = strips.run_distributed(eng, dist, 1000, halo=args.halo, min_strip_pixels=args.min_strip_pixels)
+                plan, own, exchanges = strips.run_distributed(eng, dist, 1000, halo=args.halo, min_strip_pixels=args.min_strip_pixels, level0_sweeps=l0)
             else:
-                res, exchanges = strips.run_local([eng], 1000, halo=args.halo, min_strip_pixels=args.min_strip_pixels)
+                res, exchanges = strips.run_local([eng], 1000, halo=args.halo, min_strip_pixels=args.min_strip_pixels, level0_sweeps=l0)
                 plan, own = res[0]
             ev1.record(stream)
             torch.cuda.synchronize()
@@ -132,7 +154,9 @@ def main():
             solo = rtdd.DepthDiffusion(rows, cols)
             solo.set_stream(stream)
             e1 = strips.GpuStripEngine(solo, bgr, scribble.clone(), edited.clone())
-            strips.run_local([e1], 1000, halo=args.halo)
+            if l0 > 0:
+                e1.depth[0].copy_(guess)
+            strips.run_local([e1], 1000, halo=args.halo, level0_sweeps=l0)
             torch.cuda.synchronize()
             mine = eng.depth[0][own[0]:own[1]]
             ref = e1.depth[0][own[0]:own[1]]
@@ -147,10 +171,13 @@ def main():
         per = []
         for l, (r, c) in enumerate(ctx.sizes):
             it = strips.level_iterations(1000, L, l)
+            if l0 > 0:
+                it = l0 if l == 0 else 0
             total += r * c * it
             per.append({"level": l, "size": "%dx%d" % (c, r), "sweeps": it, "split": plan[l] is not None})
-        print(json.dumps({"workload": "configs[4]: %dx%d single synthetic image, row strips + NVLink halo exchange (%s), halo %d rows%s"
-                                      % (cols, rows, "peer-memory stores + flags" if args.fused else "NCCL send/recv", args.halo, ", FUSED: halo rows pushed by the sweep kernels over peer memory" if args.fused else ""),
+        print(json.dumps({"workload": "configs[4]%s: %dx%d single synthetic image, row strips + NVLink halo exchange (%s), halo %d rows%s"
+                                      % (" (i) finest level only, %d sweeps incl. edge-weight pass and result copy" % l0 if l0 > 0 else "",
+                                         cols, rows, "peer-memory stores + flags" if args.fused else "NCCL send/recv", args.halo, ", FUSED: halo rows pushed by the sweep kernels over peer memory" if args.fused else ""),
                           "n_gpus": world, "ms_per_solve": float(t.item()), "Mpixel-sweeps/s": total / (float(t.item()) * 1e-3) / 1e6,
                           "pixel_sweeps": total, "halo_exchanges_per_solve": exchanges, "levels": per, "scaling": "strong",
                           "bit_identical_to_single_gpu": ok, "rank0_phase_ms": [[k, round(v, 4)] for k, v in phases]}), flush=True)
