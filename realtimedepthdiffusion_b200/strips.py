@@ -62,33 +62,41 @@ class Exchange:
         self.level, self.send_up, self.recv_up, self.send_dn, self.recv_dn = level, send_up, recv_up, send_dn, recv_dn
 
 
-def _solve_split_level(engine, l, rank, nranks, strips_l, iters, halo):
-    """`iters` sweeps of a level that is cut into row strips; yields an Exchange per halo exchange."""
+def _solve_split_level(engine, l, rank, nranks, strips_l, iters, halo, pass_sweeps=None):
+    """`iters` sweeps of a level that is cut into row strips; yields an Exchange per halo exchange.
+    `halo` ghost rows per open side allow `halo` sweeps between two exchanges; they run as passes of at most
+    `pass_sweeps` sweeps (default: one pass of `halo` sweeps), so e.g. halo 16 with pass_sweeps 8 halves the number of
+    exchanges while every pass keeps the kernel's best temporal block size."""
     rows = engine.sizes[l][0]
     a, b = strips_l[rank]
     w0, w1 = max(0, a - halo), min(rows, b + halo)
     engine.strip_init(l, w0, w1)
     fused = bool(getattr(engine, "fused_halo", False))
+    T = halo if (pass_sweeps is None or fused) else max(1, min(int(pass_sweeps), halo))   # the fused push is per pass
     if fused:
         # the sweep passes push their boundary rows into the neighbours' ghost rows themselves (peer memory)
         up0 = max(0, strips_l[rank - 1][0] - halo) if rank > 0 else -1
         dn0 = max(0, strips_l[rank + 1][0] - halo) if rank < nranks - 1 else -1
         engine.strip_neighbours(l, a, b, halo, up0, dn0)
     k = 0
+    since = 0                                             # sweeps since the ghost rows were last fresh
     while k < iters:
-        n = min(halo, iters - k)
+        n = min(T, iters - k, halo - since)
         if fused and l == 0 and k + n >= iters:
             engine.strip_push_enable(l, False)            # the finest level's last pass: nobody reads the ghost rows afterwards
-        engine.strip_pass(l, k, n, halo)
+        engine.strip_pass(l, k, n, T)
         k += n
+        since += n
         if fused:
             if k >= iters and l > 0:
                 engine.strip_wait(l)                      # ghost rows must be final before the prolongation reads them
+            since = 0
             yield Exchange(l, None, None, None, None)     # no data: only keeps single-process emulations in lockstep
-        elif k < iters or l > 0:                          # the last exchange feeds the prolongation
+        elif (since >= halo or k >= iters) and (k < iters or l > 0):   # the last exchange feeds the prolongation
             xk, xkm1 = engine.strip_planes(l)
             gt, gb = a - w0, w1 - b                       # ghost rows above / below
             own0, own1 = gt, gt + (b - a)
+            since = 0
             yield Exchange(l,
                            [xk[own0:own0 + halo], xkm1[own0:own0 + halo]] if gt else None,
                            [xk[0:gt], xkm1[0:gt]] if gt else None,
@@ -100,7 +108,7 @@ def _solve_split_level(engine, l, rank, nranks, strips_l, iters, halo):
         engine.strip_finish(l, a, b)                      # finest level: ghosts are stale and not needed
 
 
-def level0_coroutine(engine, rank, nranks, sweeps, halo=8):
+def level0_coroutine(engine, rank, nranks, sweeps, halo=8, pass_sweeps=None):
     """BASELINE configs[4], measurement (i) of SURVEY.md section 8d: only the finest level, a fixed number of sweeps from
     whatever guess engine.depth[0] holds, cut into `nranks` equal row strips (one rank: the ordinary level solve).
     Same per-pixel recipe and the same halo logic as the frame, so owned rows are bit-identical to one GPU."""
@@ -114,12 +122,12 @@ def level0_coroutine(engine, rank, nranks, sweeps, halo=8):
     bounds = [(r * rows) // nranks for r in range(nranks)] + [rows]
     strips0 = [(bounds[r], bounds[r + 1]) for r in range(nranks)]
     assert all(e - b >= halo for b, e in strips0), "strip shorter than the halo"
-    yield from _solve_split_level(engine, 0, rank, nranks, strips0, sweeps, halo)
+    yield from _solve_split_level(engine, 0, rank, nranks, strips0, sweeps, halo, pass_sweeps)
     mark("solve L0")
     return [strips0] + [None] * (len(engine.sizes) - 1), strips0[rank]
 
 
-def frame_coroutine(engine, rank, nranks, max_iterations, halo=8, min_strip_pixels=1 << 22, gather_result=False):
+def frame_coroutine(engine, rank, nranks, max_iterations, halo=8, min_strip_pixels=1 << 22, gather_result=False, pass_sweeps=None):
     """One solve frame on one rank; yields an Exchange whenever halo rows must move.
     The engine's level planes (depth/scribble/edited/gray) are full-size on every rank; only this rank's window of a
     split level holds meaningful depth values."""
@@ -137,7 +145,7 @@ def frame_coroutine(engine, rank, nranks, max_iterations, halo=8, min_strip_pixe
         if plan[l] is None:
             engine.solve_full(l, iters)                           # main.cpp:266
         else:
-            yield from _solve_split_level(engine, l, rank, nranks, plan[l], iters, halo)
+            yield from _solve_split_level(engine, l, rank, nranks, plan[l], iters, halo, pass_sweeps)
         mark("solve L%d" % l)
         if l > 0:
             nrows = sizes[l - 1][0]
@@ -155,14 +163,14 @@ def frame_coroutine(engine, rank, nranks, max_iterations, halo=8, min_strip_pixe
     return plan, own
 
 
-def run_distributed(engine, dist, max_iterations, halo=8, min_strip_pixels=1 << 22, level0_sweeps=0):
+def run_distributed(engine, dist, max_iterations, halo=8, min_strip_pixels=1 << 22, level0_sweeps=0, pass_sweeps=None):
     """Drive this process's rank; halo rows travel with batched isend/irecv (NCCL on GPUs, gloo on CPUs).
     level0_sweeps > 0 runs level0_coroutine (finest level only) instead of the frame."""
     rank, world = dist.get_rank(), dist.get_world_size()
     if level0_sweeps > 0:
-        co = level0_coroutine(engine, rank, world, level0_sweeps, halo)
+        co = level0_coroutine(engine, rank, world, level0_sweeps, halo, pass_sweeps)
     else:
-        co = frame_coroutine(engine, rank, world, max_iterations, halo, min_strip_pixels)
+        co = frame_coroutine(engine, rank, world, max_iterations, halo, min_strip_pixels, pass_sweeps=pass_sweeps)
     exchanges = 0
     try:
         ex = next(co)
@@ -195,13 +203,13 @@ def enable_fused_halo_local(engines):
         e.set_peers(bases[r - 1] if r > 0 else None, bases[r + 1] if r + 1 < len(engines) else None)
 
 
-def run_local(engines, max_iterations, halo=8, min_strip_pixels=1 << 22, level0_sweeps=0):
+def run_local(engines, max_iterations, halo=8, min_strip_pixels=1 << 22, level0_sweeps=0, pass_sweeps=None):
     """All ranks in one process, in lockstep (emulation on one device / CPU unit tests)."""
     n = len(engines)
     if level0_sweeps > 0:
-        cos = [level0_coroutine(e, r, n, level0_sweeps, halo) for r, e in enumerate(engines)]
+        cos = [level0_coroutine(e, r, n, level0_sweeps, halo, pass_sweeps) for r, e in enumerate(engines)]
     else:
-        cos = [frame_coroutine(e, r, n, max_iterations, halo, min_strip_pixels) for r, e in enumerate(engines)]
+        cos = [frame_coroutine(e, r, n, max_iterations, halo, min_strip_pixels, pass_sweeps=pass_sweeps) for r, e in enumerate(engines)]
     results = [None] * n
     pending = [None] * n
     live = set(range(n))

@@ -55,6 +55,23 @@ def test_lockstep_strips_are_bit_identical_to_the_single_solve(rows, cols, nrank
     assert np.array_equal(got, want)
 
 
+@pytest.mark.parametrize("rows,cols,nranks,halo,pass_sweeps,iters", [(203, 150, 2, 8, 4, 70), (256, 96, 3, 16, 8, 100), (181, 130, 2, 9, 4, 33)])
+def test_several_passes_per_exchange_are_bit_identical(rows, cols, nranks, halo, pass_sweeps, iters):
+    """`halo` ghost rows, passes of `pass_sweeps` sweeps: one exchange per `halo` sweeps instead of one per pass."""
+    bgr, scribble, edited = synth.synth_case(rows, cols, 77)
+    want_state = ob.FrameState(bgr)
+    want_state.solve(scribble, edited, iters)
+    engines = [CpuStripEngine(bgr, scribble, edited) for _ in range(nranks)]
+    results, exchanges = strips.run_local(engines, iters, halo=halo, min_strip_pixels=1, pass_sweeps=pass_sweeps)
+    engines1 = [CpuStripEngine(bgr, scribble, edited) for _ in range(nranks)]
+    _, exchanges1 = strips.run_local(engines1, iters, halo=pass_sweeps, min_strip_pixels=1)
+    assert 0 < exchanges < exchanges1
+    gotf = np.zeros_like(want_state.depth[0])
+    for r, (plan, own) in enumerate(results):
+        gotf[own[0]:own[1]] = engines[r].st.depth[0][own[0]:own[1]]
+    assert np.array_equal(gotf.view(np.uint32), want_state.depth[0].view(np.uint32))
+
+
 @pytest.mark.parametrize("rows,cols,nranks,halo,sweeps", [(203, 150, 2, 4, 19), (256, 96, 4, 8, 64), (181, 130, 3, 5, 3)])
 def test_level0_only_strips_match_the_single_level_solve(rows, cols, nranks, halo, sweeps):
     """configs[4] measurement (i): a fixed number of finest-level sweeps, strip-decomposed, from the same guess."""

@@ -76,6 +76,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--halo", type=int, default=8)
+    ap.add_argument("--pass-sweeps", type=int, default=0, help="sweeps per pass when smaller than --halo: several passes between two exchanges (NCCL mode)")
     ap.add_argument("--min-strip-pixels", type=int, default=1 << 22)
     ap.add_argument("--check", action="store_true")
     ap.add_argument("--fused", action="store_true", help="halo rows pushed by the sweep kernels over peer memory instead of NCCL send/recv")
@@ -99,13 +100,14 @@ def main():
             eng.enable_fused_halo_distributed(dist)
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = args.level0_sweeps
+        ps = args.pass_sweeps or None
         guess = None
         if l0 > 0:
             # the guess the finest level really starts from: one untimed whole-pyramid frame up to the prolongation
             if world > 1:
-                strips.run_distributed(eng, dist, 1000, halo=args.halo, min_strip_pixels=args.min_strip_pixels)
+                strips.run_distributed(eng, dist, 1000, halo=args.halo, min_strip_pixels=args.min_strip_pixels, pass_sweeps=ps)
             else:
-                strips.run_local([eng], 1000, halo=args.halo, min_strip_pixels=args.min_strip_pixels)
+                strips.run_local([eng], 1000, halo=args.halo, min_strip_pixels=args.min_strip_pixels, pass_sweeps=ps)
             if world > 1:                                        # every rank needs all rows of the guess: take rank order
                 rows0 = eng.depth[0].shape[0]
                 b = [(r * rows0) // world for r in range(world)] + [rows0]
@@ -127,9 +129,9 @@ def main():
                 dist.barrier()
             ev0.record(stream)
             if world > 1:
-                plan, own, exchanges = strips.run_distributed(eng, dist, 1000, halo=args.halo, min_strip_pixels=args.min_strip_pixels, level0_sweeps=l0)
+                plan, own, exchanges = strips.run_distributed(eng, dist, 1000, halo=args.halo, min_strip_pixels=args.min_strip_pixels, level0_sweeps=l0, pass_sweeps=ps)
             else:
-                res, exchanges = strips.run_local([eng], 1000, halo=args.halo, min_strip_pixels=args.min_strip_pixels, level0_sweeps=l0)
+                res, exchanges = strips.run_local([eng], 1000, halo=args.halo, min_strip_pixels=args.min_strip_pixels, level0_sweeps=l0, pass_sweeps=ps)
                 plan, own = res[0]
             ev1.record(stream)
             torch.cuda.synchronize()
@@ -156,7 +158,7 @@ def main():
             e1 = strips.GpuStripEngine(solo, bgr, scribble.clone(), edited.clone())
             if l0 > 0:
                 e1.depth[0].copy_(guess)
-            strips.run_local([e1], 1000, halo=args.halo, level0_sweeps=l0)
+            strips.run_local([e1], 1000, halo=args.halo, level0_sweeps=l0, pass_sweeps=ps)
             torch.cuda.synchronize()
             mine = eng.depth[0][own[0]:own[1]]
             ref = e1.depth[0][own[0]:own[1]]
@@ -177,7 +179,8 @@ def main():
             per.append({"level": l, "size": "%dx%d" % (c, r), "sweeps": it, "split": plan[l] is not None})
         print(json.dumps({"workload": "configs[4]%s: %dx%d single synthetic image, row strips + NVLink halo exchange (%s), halo %d rows%s"
                                       % (" (i) finest level only, %d sweeps incl. edge-weight pass and result copy" % l0 if l0 > 0 else "",
-                                         cols, rows, "peer-memory stores + flags" if args.fused else "NCCL send/recv", args.halo, ", FUSED: halo rows pushed by the sweep kernels over peer memory" if args.fused else ""),
+                                         cols, rows, "peer-memory stores + flags" if args.fused else "NCCL send/recv", args.halo, (", FUSED: halo rows pushed by the sweep kernels over peer memory" if args.fused else "")
+                                         + (", passes of %d sweeps" % ps if ps else "")),
                           "n_gpus": world, "ms_per_solve": float(t.item()), "Mpixel-sweeps/s": total / (float(t.item()) * 1e-3) / 1e6,
                           "pixel_sweeps": total, "halo_exchanges_per_solve": exchanges, "levels": per, "scaling": "strong",
                           "bit_identical_to_single_gpu": ok, "rank0_phase_ms": [[k, round(v, 4)] for k, v in phases]}), flush=True)
