@@ -5,6 +5,7 @@
 // ref: src/GPUImageProcessing.cu:8-100; src/main.cpp:111-112,143-145,272-279,290.
 
 #include "rtdd_internal.h"
+#include "pyrup_device.h"
 
 namespace rtdd {
 
@@ -292,21 +293,6 @@ cudaError_t launch_pyrdown_gray(cudaStream_t s, const uint8_t *src, size_t srcPi
 // OpenCV's unfused CPU path and to oracle_pyrup_f32.
 // ref: src/main.cpp:272-279
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ float pyrup_h(const float *__restrict__ s, int n, int dx)
-{
-    // horizontal pass value at destination column dx of one source row
-    if (n == 1) return __fmul_rn(__ldg(s), 8.0f);
-    if (dx >= 2 * n) dx = 2 * n - 1;                       // odd destination width: repeat last column
-    const int x = dx >> 1;
-    if (dx & 1) {
-        if (x == n - 1) return __fmul_rn(__ldg(s + x), 8.0f);
-        return __fmul_rn(__fadd_rn(__ldg(s + x), __ldg(s + x + 1)), 4.0f);
-    }
-    if (x == 0) return __fadd_rn(__fmul_rn(__ldg(s), 6.0f), __fmul_rn(__ldg(s + 1), 2.0f));
-    if (x == n - 1) return __fadd_rn(__ldg(s + x - 1), __fmul_rn(__ldg(s + x), 7.0f));
-    return __fadd_rn(__fadd_rn(__ldg(s + x - 1), __fmul_rn(__ldg(s + x), 6.0f)), __ldg(s + x + 1));
-}
-
 __global__ void __launch_bounds__(256)
 pyrup_depth_kernel(const float *__restrict__ src, size_t srcPitch, int srows, int scols,
                    float *__restrict__ dst, size_t dstPitch, int drows, int dcols, int dy0)
@@ -335,15 +321,6 @@ pyrup_depth_kernel(const float *__restrict__ src, size_t srcPitch, int srows, in
 // Interior fast path: one thread produces destination columns 4j..4j+3 of the row pair (2y, 2y+1) from source
 // columns 2j-1..2j+2 of source rows y-1, y, y+1 -- the same expressions, in the same order, as pyrup_h and the scalar
 // kernel (bit-identical); border columns / rows and odd-sized destinations go through the scalar expressions.
-__device__ __forceinline__ void pyrup_h4(const float *__restrict__ s, int j, float (&r)[4])
-{
-    const float a = __ldg(s + 2 * j - 1), b = __ldg(s + 2 * j), c = __ldg(s + 2 * j + 1), d = __ldg(s + 2 * j + 2);
-    r[0] = __fadd_rn(__fadd_rn(a, __fmul_rn(b, 6.0f)), c);
-    r[1] = __fmul_rn(__fadd_rn(b, c), 4.0f);
-    r[2] = __fadd_rn(__fadd_rn(b, __fmul_rn(c, 6.0f)), d);
-    r[3] = __fmul_rn(__fadd_rn(c, d), 4.0f);
-}
-
 __global__ void __launch_bounds__(256)
 pyrup_depth4_kernel(const float *__restrict__ src, size_t srcPitch, int srows, int scols,
                     float *__restrict__ dst, size_t dstPitch, int drows, int dcols, int rowBegin, int rowEnd)

@@ -208,7 +208,16 @@ struct LevelArgs {
     const uint8_t *scribble; size_t scribblePitch;
     const uint8_t *gray; size_t grayPitch;
     uint8_t *u8; size_t u8Pitch;          // optional quantised output (whole-frame path, level 0)
+    // whole-frame path, levels below the coarsest: the guess is the prolongation of `coarse` with the level's Dirichlet
+    // values re-injected from `edited`; it is produced inside the level set-up instead of being read from `depth`
+    const float *coarse; size_t coarsePitch; int coarseRows, coarseCols;
+    const uint8_t *edited; size_t editedPitch;
 };
+
+// Opt-in (rtdd_set_tuning("fused_prolong", 1)): bit-identical and tested, but measured no faster than the three separate
+// kernels inside the frame graph (4K 1.9025 vs 1.8945 ms, 8K UHD 3.081 vs 3.065 ms, 1080p 1.306 vs 1.307 ms): with
+// programmatic dependent launch the small kernels already overlap, and the 66 MB saved at 4K are ~1 % of a frame.
+static int g_fusedProlong = 0;
 
 // One level on stream `s`: edge-weight pass, sweeps, result into the caller's depth plane.  `capturing` selects
 // the event-record flavour that is legal inside a stream capture.
@@ -218,15 +227,21 @@ int enqueue_level(rtdd_ctx *ctx, cudaStream_t s, const LevelArgs &a, bool captur
     const bool coarsest = (a.level == ctx->levels - 1);
     const int threshold = (a.level == 0) ? 0 : 4;          // ref: src/GPUSolver.cu:201-202
     int n = 0;
-    RTDD_TRY(rtdd::launch_level_init(s, L, a.depth, a.depthPitch, a.scribble, a.scribblePitch, a.gray, a.grayPitch, coarsest, threshold, L.x[0]),
-             "level init");
+    unsigned int *resetResidual = (a.iters > 0) ? L.dResidual : nullptr;     // the set-up kernel zeroes the level's residual word
+    if (a.coarse) {
+        // ref: src/main.cpp:272-281 + src/GPUSolver.cu:290-293 in one pass; the guess itself is never stored as a pitched plane
+        RTDD_TRY(rtdd::launch_level_prolong_init(s, L, a.coarse, a.coarsePitch, a.coarseRows, a.coarseCols, a.edited, a.editedPitch,
+                                                 a.scribble, a.scribblePitch, a.gray, a.grayPitch, threshold, L.x[0], resetResidual), "level prolong+init");
+    } else {
+        RTDD_TRY(rtdd::launch_level_init(s, L, a.depth, a.depthPitch, a.scribble, a.scribblePitch, a.gray, a.grayPitch, coarsest, threshold, L.x[0],
+                                         resetResidual), "level init");
+    }
     n++;
     int plane = 0;
     bool direct = false;
     if (a.iters > 0) {
         direct = target_ok(a.depth, a.depthPitch);
         rtdd::SweepTarget tgt = {direct ? a.depth : nullptr, (int)(a.depthPitch / sizeof(float)), direct ? a.u8 : nullptr, (int)a.u8Pitch, L.dResidual};
-        RTDD_TRY(cudaMemsetAsync(L.dResidual, 0, sizeof(unsigned int), s), "residual reset");
         const unsigned int flags = capturing ? cudaEventRecordExternal : cudaEventRecordDefault;
         RTDD_TRY(cudaEventRecordWithFlags(L.evBegin, s, flags), "level event");
         int k = 0;
@@ -447,6 +462,13 @@ int rtdd_set_tuning(rtdd_ctx *ctx, const char *key, int value)
         destroy_graphs(ctx);
         return 0;
     }
+    if (strcmp(key, "fused_prolong") == 0 && (value == 0 || value == 1)) {
+        g_fusedProlong = value;
+        DeviceGuard guard(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+        destroy_graphs(ctx);
+        return 0;
+    }
     if (strcmp(key, "resident_two_sweep") == 0 && (value == 0 || value == 1)) {
         rtdd::set_resident_two_sweep(value);
         DeviceGuard guard(ctx->device);
@@ -514,7 +536,7 @@ int rtdd_solve_level(rtdd_ctx *ctx, float *depth, size_t depthPitch, const uint8
     key.kind = 1; key.level = level; key.iters = maxIterations; key.variant = variant; key.T = T;
     key.p[0] = depth; key.p[1] = scribble; key.p[2] = gray;
     key.pitch[0] = depthPitch; key.pitch[1] = scribblePitch; key.pitch[2] = grayPitch;
-    const LevelArgs args{level, maxIterations, depth, depthPitch, scribble, scribblePitch, gray, grayPitch, nullptr, 0};
+    const LevelArgs args{level, maxIterations, depth, depthPitch, scribble, scribblePitch, gray, grayPitch, nullptr, 0, nullptr, 0, 0, 0, nullptr, 0};
     return run_cached_graph(ctx, key, [&](cudaStream_t cs, int *kernels) { return enqueue_level(ctx, cs, args, true, kernels); });
 }
 
@@ -1071,21 +1093,33 @@ static int frame_solve_from(rtdd_ctx *ctx, int maxIterations, int startLevel)
             RTDD_TRY(rtdd::launch_convert(cs, F.edited, F.editedPitch, F.depth, F.depthPitch, F.scribble, F.scribblePitch, F.rows, F.cols), "frame: convert");
             n++;
         }
+        bool fuseNext = false;
         for (int l = Lc; l >= 0; l--) {                                           // main.cpp:261-288
             RtddFrameLevel &F = ctx->fl[l];
             const int iters = rtdd_level_iterations(maxIterations, ctx->levels, l);
             // level 0 also emits the 8-bit map (main.cpp:290) from its last sweep pass
-            const LevelArgs args{l, iters, F.depth, F.depthPitch, F.scribble, F.scribblePitch, F.gray, F.grayPitch,
-                                 l == 0 ? ctx->depthU8 : nullptr, l == 0 ? ctx->depthU8Pitch : 0};
+            LevelArgs args{l, iters, F.depth, F.depthPitch, F.scribble, F.scribblePitch, F.gray, F.grayPitch,
+                           l == 0 ? ctx->depthU8 : nullptr, l == 0 ? ctx->depthU8Pitch : 0, nullptr, 0, 0, 0, nullptr, 0};
+            if (fuseNext) {
+                // this level's guess = prolongation of the level above + its own Dirichlet values, formed by its set-up kernel
+                RtddFrameLevel &C = ctx->fl[l + 1];
+                args.coarse = C.depth; args.coarsePitch = C.depthPitch; args.coarseRows = C.rows; args.coarseCols = C.cols;
+                args.edited = F.edited; args.editedPitch = F.editedPitch;
+            }
             int k = 0;
             const int r = enqueue_level(ctx, cs, args, true, &k);
             if (r) return r;
             n += k;
+            fuseNext = false;
             if (l > 0) {
                 RtddFrameLevel &N = ctx->fl[l - 1];
-                RTDD_TRY(rtdd::launch_pyrup_depth(cs, F.depth, F.depthPitch, F.rows, F.cols, N.depth, N.depthPitch, N.rows, N.cols), "frame: pyrUp");
-                RTDD_TRY(rtdd::launch_convert(cs, N.edited, N.editedPitch, N.depth, N.depthPitch, N.scribble, N.scribblePitch, N.rows, N.cols), "frame: convert");
-                n += 2;
+                // a level without sweeps must leave its guess in its depth plane: keep the separate kernels for it
+                fuseNext = g_fusedProlong && rtdd_level_iterations(maxIterations, ctx->levels, l - 1) > 0 && target_ok(N.depth, N.depthPitch);
+                if (!fuseNext) {
+                    RTDD_TRY(rtdd::launch_pyrup_depth(cs, F.depth, F.depthPitch, F.rows, F.cols, N.depth, N.depthPitch, N.rows, N.cols), "frame: pyrUp");
+                    RTDD_TRY(rtdd::launch_convert(cs, N.edited, N.editedPitch, N.depth, N.depthPitch, N.scribble, N.scribblePitch, N.rows, N.cols), "frame: convert");
+                    n += 2;
+                }
             }
         }
         *kernels = n;

@@ -132,9 +132,12 @@ struct HaloPush {
     const unsigned int *waitUp, *waitDn;   // this rank's flags: spin until >= waitValue before touching ghost rows (0 = no wait)
     unsigned int waitValue;
 };
+cudaError_t launch_level_prolong_init(cudaStream_t s, const RtddLevel &L, const float *src, size_t srcPitch, int srows, int scols,
+                                      const uint8_t *edited, size_t editedPitch, const uint8_t *scribble, size_t scribblePitch,
+                                      const uint8_t *gray, size_t grayPitch, int threshold, float *x0, unsigned int *residual);
 cudaError_t launch_level_init(cudaStream_t s, const RtddLevel &L, const float *depth, size_t depthPitch,
                               const uint8_t *scribble, size_t scribblePitch,
-                              const uint8_t *gray, size_t grayPitch, bool coarsest, int threshold, float *x0);
+                              const uint8_t *gray, size_t grayPitch, bool coarsest, int threshold, float *x0, unsigned int *residual = nullptr);
 cudaError_t launch_sweep_single(cudaStream_t s, const RtddLevel &L, const float *lut, const float *x, const float *prev,
                                 float *out, float omega, float gamma, bool firstSweep, const SweepTarget *target = nullptr);
 // temporally blocked: T sweeps (x, prev) -> (xOut, prevOut); omegas passed by value (<= RTDD_MAX_T)

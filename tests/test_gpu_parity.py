@@ -467,6 +467,37 @@ def test_frame_solve_host_vs_oracle(rtdd, rows, cols, iters):
     ctx.close()
 
 
+@pytest.mark.parametrize("rows,cols,levels,iters", [(46, 91, 2, 40), (203, 317, 3, 120), (271, 481, 3, 64), (270, 480, 3, 64), (1080, 1920, None, 300),
+                                                   (129, 257, 4, 33), (560, 700, None, 7)])
+def test_fused_prolongation_equals_the_three_separate_kernels(rtdd, rows, cols, levels, iters):
+    """The fused prolongation + Dirichlet injection + edge-weight pass (frame path, ref: src/main.cpp:272-281 +
+    src/GPUSolver.cu:290-293) against pyrUp -> convert -> level set-up run separately: every level's depth plane, the 8-bit
+    map, odd and even sizes, levels with and without sweeps (small iteration counts give some levels 0 sweeps)."""
+    bgr, scribble, edited = synth.synth_case(rows, cols, rows + cols)
+    planes = {}
+    for fused in (1, 0):
+        ctx = rtdd.DepthDiffusion(rows, cols, levels)
+        ctx.set_tuning("fused_prolong", fused)
+        ctx.frame_set_image(bgr)
+        u8 = ctx.frame_solve_host(scribble, edited, iters, np.zeros((rows, cols), np.uint8)).numpy().copy()
+        ev = synth.brush_events(rows, cols, 11, 2, 6)
+        for e in ev:
+            ctx.frame_paint(*e)                       # second frame: state carried over, device-resident strokes
+        ctx.frame_solve(iters)
+        ctx.sync()
+        planes[fused] = [u8, ctx.frame_plane(ctx.PLANE_DEPTH_U8, 0).cpu().numpy().copy()] + \
+                        [ctx.frame_plane(ctx.PLANE_DEPTH, l).cpu().numpy().copy() for l in range(ctx.levels)]
+        ctx.set_tuning("fused_prolong", 0)
+        ctx.close()
+    for a, b in zip(planes[1], planes[0]):
+        assert a.shape == b.shape
+        assert np.array_equal(a.view(np.uint8), b.view(np.uint8))
+    if rows * cols <= 203 * 317 and levels is not None:
+        st = ob.FrameState(bgr, levels)
+        want = st.solve(scribble, edited, iters)
+        assert np.array_equal(planes[1][0], want)
+
+
 # ---- golden vectors recorded from the reference on a B200 ---------------------------------------
 
 @pytest.mark.parametrize("name", ["synth_tiny", "synth_small", "synth_odd", "dog", "womanparasol"])
