@@ -245,6 +245,12 @@ def run_native(args, dist, rank, world, local):
             ms = t_eff(lambda: L.rtdd_effects_fused(ctx._h, b[0], b[1], g[0], g[1], d[0], d[1], o[0][0], o[0][1], o[1][0], o[1][1],
                                                     o[2][0], o[2][1], rows, cols))
             eff["fused_all_three"] = {"ms": ms, "GB/s": 17.0 * px / ms / 1e6}
+            # the frame context knows its image is unchanged between frames: summed-area table built once per image
+            ms = t_eff(lambda: L.rtdd_frame_effects(ctx._h, o[0][0], o[0][1], o[1][0], o[1][1], o[2][0], o[2][1]))
+            eff["frame_effects_cached_table"] = {"ms": ms, "GB/s": 17.0 * px / ms / 1e6}
+            # configs[2] as one per-frame step: solve + the three effects, device-resident
+            ms = t_eff(lambda: (ctx.frame_solve(1000), L.rtdd_frame_effects(ctx._h, o[0][0], o[0][1], o[1][0], o[1][1], o[2][0], o[2][1])), reps=10)
+            eff["solve_plus_effects_frame"] = {"ms": ms}
 
     # ---- configs[3] on one GPU: several independent images in flight (one context + stream each).  The coarse levels
     #      occupy <= 16 SMs for most of their 1500 sweeps, so other images' levels fill the rest of the GPU.

@@ -231,6 +231,10 @@ int rtdd_frame_solve(rtdd_ctx *ctx, int maxIterations);
  * `coarsestLevel` starts from ITS OWN previous solution with the current annotations re-imposed and runs its scheduled
  * sweeps; finer levels proceed as in rtdd_frame_solve.  coarsestLevel = levels-1 is exactly rtdd_frame_solve. */
 int rtdd_frame_solve_incremental(rtdd_ctx *ctx, int maxIterations, int coarsestLevel);
+/* ref: src/main.cpp:190-230 -- desaturation / haze / defocus of the frame image by the frame's solved depth, written to
+ * caller-owned DEVICE planes (BGR u8, byte pitches; any of the three may be NULL).  The defocus summed-area table depends
+ * on the image only and is built once per rtdd_frame_set_image, not once per call. */
+int rtdd_frame_effects(rtdd_ctx *ctx, uint8_t *desat, size_t desatPitch, uint8_t *haze, size_t hazePitch, uint8_t *defocus, size_t defocusPitch);
 /* ref: src/main.cpp:46-62 -- brush stroke into the context's level-0 annotation planes */
 int rtdd_frame_paint(rtdd_ctx *ctx, int x, int y, int scribbleColor, int scribbleRadius);
 /* device pointers/pitches of the context-owned planes (for effects, tests, downloads) */

@@ -68,6 +68,7 @@ SIGNATURES = {
     "rtdd_frame_solve": (i32, [vp, i32]),
     "rtdd_frame_paint": (i32, [vp, i32, i32, i32, i32]),
     "rtdd_frame_plane": (i32, [vp, i32, i32, C.POINTER(vp), C.POINTER(sz), C.POINTER(i32), C.POINTER(i32)]),
+    "rtdd_frame_effects": (i32, [vp, vp, sz, vp, sz, vp, sz]),
 }
 
 # the reference-named C++ shims (Itanium-mangled), same ten functions as include/GPU*.h

@@ -243,6 +243,11 @@ class DepthDiffusion:
     def frame_paint(self, x, y, color, radius):
         self._ck(lib.rtdd_frame_paint(self._h, int(x), int(y), int(color), int(radius)))
 
+    def frame_effects(self, desat=None, haze=None, defocus=None):
+        """GPUSimulateDesaturation / Haze / Defocus on the frame's own image and solved depth (ref: src/main.cpp:190-230);
+        outputs are device BGR planes, any may be None.  The defocus summed-area table is cached per image."""
+        self._ck(lib.rtdd_frame_effects(self._h, _ptr(desat), _pitch(desat), _ptr(haze), _pitch(haze), _ptr(defocus), _pitch(defocus)))
+
     PLANE_DEPTH, PLANE_GRAY, PLANE_SCRIBBLE, PLANE_EDITED, PLANE_BGR, PLANE_DEPTH_U8 = range(6)
 
     def frame_plane(self, which, level=0):

@@ -933,6 +933,7 @@ int rtdd_defocus(rtdd_ctx *ctx, const uint8_t *orig, size_t origPitch, const flo
     DeviceGuard guard(ctx->device);
     int rc = ensure_sat(ctx, rows, cols);
     if (rc) return rc;
+    ctx->frameSatValid = false;            // the scratch is about to hold the table of the caller's image
     int launched = 0;
     RTDD_TRY(rtdd::launch_defocus(ctx->stream, ctx->satScratch, orig, origPitch, nullptr, 0, depth, depthPitch, out, outPitch,
                                   nullptr, 0, nullptr, 0, rows, cols, &launched), "rtdd_defocus");
@@ -950,6 +951,7 @@ int rtdd_effects_fused(rtdd_ctx *ctx, const uint8_t *orig, size_t origPitch, con
     DeviceGuard guard(ctx->device);
     int rc = ensure_sat(ctx, rows, cols);
     if (rc) return rc;
+    ctx->frameSatValid = false;
     int launched = 0;
     RTDD_TRY(rtdd::launch_defocus(ctx->stream, ctx->satScratch, orig, origPitch, gray, grayPitch, depth, depthPitch, defocus, defocusPitch,
                                   desat, desatPitch, haze, hazePitch, rows, cols, &launched), "rtdd_effects_fused");
@@ -1065,6 +1067,7 @@ int rtdd_frame_set_image(rtdd_ctx *ctx, const uint8_t *bgrHost, size_t bgrPitch)
         ctx->launches++;
     }
     ctx->imageSet = true;
+    ctx->frameSatValid = false;
     return 0;
 }
 
@@ -1160,6 +1163,44 @@ int rtdd_frame_solve_host(rtdd_ctx *ctx, const uint8_t *scribbleHost, size_t scr
         RTDD_TRY(cudaMemcpy2DAsync(depthU8Host, depthU8Pitch, ctx->depthU8, ctx->depthU8Pitch, (size_t)ctx->cols, ctx->rows, cudaMemcpyDeviceToHost, s),
                  "rtdd_frame_solve_host (download)");                          // main.cpp:291
         RTDD_TRY(cudaStreamSynchronize(s), "rtdd_frame_solve_host");
+    }
+    return 0;
+}
+
+// The three depth effects on the frame's own planes (level-0 image, gray, solved depth).  The image of a frame context
+// only changes in rtdd_frame_set_image, so the defocus summed-area table is built once per image and reused by every later
+// call -- main.cpp re-applies the effects to the same image after every solve (ref: src/main.cpp:190-230).
+int rtdd_frame_effects(rtdd_ctx *ctx, uint8_t *desat, size_t desatPitch, uint8_t *haze, size_t hazePitch, uint8_t *defocus, size_t defocusPitch)
+{
+    if (!ctx) return RTDD_E_ARG;
+    if (!ctx->imageSet) return rtdd_fail(ctx, RTDD_E_STATE, "rtdd_frame_effects");
+    const size_t rowBytes = (size_t)ctx->cols * 3;
+    if ((desat && desatPitch < rowBytes) || (haze && hazePitch < rowBytes) || (defocus && defocusPitch < rowBytes))
+        return rtdd_fail(ctx, RTDD_E_ARG, "rtdd_frame_effects");
+    DeviceGuard guard(ctx->device);
+    cudaStream_t s = ctx->stream;
+    RtddFrameLevel &F = ctx->fl[0];
+    const int rows = ctx->rows, cols = ctx->cols;
+    if (defocus) {
+        int rc = ensure_sat(ctx, rows, cols);
+        if (rc) return rc;
+        const bool build = !ctx->frameSatValid;
+        const bool all = desat && haze;
+        int launched = 0;
+        RTDD_TRY(rtdd::launch_defocus(s, ctx->satScratch, ctx->bgr, ctx->bgrPitch, all ? F.gray : nullptr, all ? F.grayPitch : 0, F.depth, F.depthPitch,
+                                      defocus, defocusPitch, all ? desat : nullptr, desatPitch, all ? haze : nullptr, hazePitch, rows, cols, &launched, build),
+                 "rtdd_frame_effects (defocus)");
+        ctx->frameSatValid = true;
+        ctx->launches += launched;
+        if (all) return 0;
+    }
+    if (desat) {
+        RTDD_TRY(rtdd::launch_desaturate(s, ctx->bgr, ctx->bgrPitch, F.gray, F.grayPitch, F.depth, F.depthPitch, desat, desatPitch, rows, cols), "rtdd_frame_effects (desaturation)");
+        ctx->launches++;
+    }
+    if (haze) {
+        RTDD_TRY(rtdd::launch_haze(s, ctx->bgr, ctx->bgrPitch, F.depth, F.depthPitch, haze, hazePitch, rows, cols), "rtdd_frame_effects (haze)");
+        ctx->launches++;
     }
     return 0;
 }

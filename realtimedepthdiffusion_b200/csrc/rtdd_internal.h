@@ -96,6 +96,7 @@ struct rtdd_ctx {
     uint8_t *bgr = nullptr; size_t bgrPitch = 0;
     uint8_t *depthU8 = nullptr; size_t depthU8Pitch = 0;
     bool imageSet = false;
+    bool frameSatValid = false;        // satScratch holds the summed-area table of the frame image (rtdd_frame_effects)
     // defocus scratch (summed-area tables), grown on demand
     void *satScratch = nullptr; size_t satBytes = 0;
 };
@@ -208,9 +209,10 @@ cudaError_t launch_haze(cudaStream_t s, const uint8_t *orig, size_t origPitch, c
 int defocus_kernel_size(int rows, int cols);
 size_t defocus_scratch_bytes(int rows, int cols);
 // desat/haze may be null (defocus only); returns number of kernels launched through *launched
+cudaError_t launch_sat_build(cudaStream_t s, void *scratch, const uint8_t *orig, size_t origPitch, int rows, int cols);
 cudaError_t launch_defocus(cudaStream_t s, void *scratch, const uint8_t *orig, size_t origPitch, const uint8_t *gray, size_t grayPitch,
                            const float *depth, size_t depthPitch, uint8_t *defocus, size_t defocusPitch,
                            uint8_t *desat, size_t desatPitch, uint8_t *haze, size_t hazePitch,
-                           int rows, int cols, int *launched);
+                           int rows, int cols, int *launched, bool buildSat = true);
 
 }  // namespace rtdd

@@ -8,16 +8,19 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+def _build_native():
+    """Make sure the native pieces exist and are newer than their sources BEFORE any test module imports the package
+    (importing it loads librtdd.so and fails loudly without it).  The recipe is loaded by path for the same reason."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("rtdd_build_recipe", os.path.join(ROOT, "realtimedepthdiffusion_b200", "build.py"))
+    recipe = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(recipe)
+    recipe.build_all()
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
-
-
-@pytest.fixture(scope="session", autouse=True)
-def _built():
-    """Make sure the native pieces exist (no-op when they are up to date)."""
-    from realtimedepthdiffusion_b200 import build
-    build.build_all()
-    yield
+    _build_native()
 
 
 def pytest_collection_modifyitems(config, items):

@@ -498,6 +498,54 @@ def test_fused_prolongation_equals_the_three_separate_kernels(rtdd, rows, cols, 
         assert np.array_equal(planes[1][0], want)
 
 
+@pytest.mark.parametrize("rows,cols,iters", [(203, 317, 60), (360, 641, 40)])
+def test_frame_effects_with_cached_summed_area_table(rtdd, rows, cols, iters):
+    """rtdd_frame_effects (ref: src/main.cpp:190-230 on the frame's own planes) equals the three stand-alone effect
+    calls; the defocus table is built once per image and must be rebuilt after a new image or after a stand-alone defocus
+    call borrowed the scratch."""
+    ctx = rtdd.DepthDiffusion(rows, cols)
+    other_bgr, _, other_depth = effect_inputs(rows, cols, 5)
+    for seed in (77, 78):                                      # second round: a NEW image in the same context
+        bgr, scribble, edited = synth.synth_case(rows, cols, seed)
+        ctx.frame_set_image(bgr)
+        for frame in range(2):                                 # second frame of an image: cached table, new depth
+            if frame == 1:
+                for e in synth.brush_events(rows, cols, seed, 2, 4):
+                    ctx.frame_paint(*e)
+                ctx.frame_solve(iters)
+            else:
+                ctx.frame_solve_host(scribble, edited, iters, np.zeros((rows, cols), np.uint8))
+            depth = ctx.frame_plane(ctx.PLANE_DEPTH, 0).cpu().numpy()
+            gray = ctx.frame_plane(ctx.PLANE_GRAY, 0).cpu().numpy()[:rows, :cols]
+            o, g, d = to_dev(bgr, 3), to_dev(np.ascontiguousarray(gray)), to_dev(depth)
+            want = [to_dev(np.zeros_like(bgr), 3) for _ in range(3)]
+            helper = rtdd.DepthDiffusion(rows, cols, 1)
+            helper.simulate_desaturation(o, g, d, want[0])
+            helper.simulate_haze(o, d, want[1])
+            helper.simulate_defocus(o, d, want[2])
+            helper.sync()
+            helper.close()
+            got = [to_dev(np.zeros_like(bgr), 3) for _ in range(3)]
+            ctx.frame_effects(got[0], got[1], got[2])
+            ctx.sync()
+            for a, b in zip(got, want):
+                assert np.array_equal(to_host(a, 3), to_host(b, 3))
+            only = to_dev(np.zeros_like(bgr), 3)
+            ctx.frame_effects(None, None, only)                # defocus alone, table already there
+            ctx.sync()
+            assert np.array_equal(to_host(only, 3), to_host(want[2], 3))
+            # a stand-alone defocus of ANOTHER image through the same context overwrites the scratch ...
+            scratch_user = to_dev(np.zeros_like(bgr), 3)
+            ctx.simulate_defocus(to_dev(other_bgr, 3), to_dev(other_depth), scratch_user)
+            again = [to_dev(np.zeros_like(bgr), 3) for _ in range(2)]
+            ctx.frame_effects(again[0], None, again[1])        # ... so the frame's table is rebuilt here
+            ctx.sync()
+            assert np.array_equal(to_host(again[1], 3), to_host(want[2], 3))
+            assert np.array_equal(to_host(again[0], 3), to_host(want[0], 3))
+            assert np.array_equal(to_host(scratch_user, 3), ob.defocus(other_bgr, other_depth))
+    ctx.close()
+
+
 # ---- golden vectors recorded from the reference on a B200 ---------------------------------------
 
 @pytest.mark.parametrize("name", ["synth_tiny", "synth_small", "synth_odd", "dog", "womanparasol"])
