@@ -157,6 +157,13 @@ int rtdd_arena(rtdd_ctx *ctx, void **base, size_t *bytes);
 int rtdd_strip_set_peers(rtdd_ctx *ctx, void *arenaAbove, void *arenaBelow);
 int rtdd_strip_neighbours(rtdd_ctx *ctx, int level, int ownBegin, int ownEnd, int halo, int aboveWinBegin, int belowWinBegin);
 int rtdd_strip_wait(rtdd_ctx *ctx, int level);
+/* Staged peer exchange (rtdd_set_tuning("strip_peer_staging", 1) before rtdd_strip_neighbours): the passes stay the plain
+ * sweep kernels; rtdd_strip_push copies the `halo` rows next to each strip boundary into the neighbours' staging areas
+ * (peer memory) and raises their sequence flags, rtdd_strip_pull waits for the neighbours' flags and unpacks the staged
+ * rows into this rank's ghost rows.  Call push, then pull, once per exchange; every rank must do the same number of
+ * exchanges per level.  No NCCL call, no host round trip. */
+int rtdd_strip_push(rtdd_ctx *ctx, int level);
+int rtdd_strip_pull(rtdd_ctx *ctx, int level);
 /* on = 0: the following passes of `level` keep their boundary rows to themselves (the finest level's last pass: nobody
  * reads the ghost rows afterwards); the flags are still raised.  Reset to on by rtdd_strip_neighbours. */
 int rtdd_strip_push_enable(rtdd_ctx *ctx, int level, int on);

@@ -353,6 +353,7 @@ int rtdd_create(int rows, int cols, int levels, int device, rtdd_ctx **out)
         L.pitchB = (int)rtdd_round_up((size_t)L.cols + 4, 128);
         total += 4 * rtdd_round_up((size_t)L.pitchF * L.rows * sizeof(float), 256);
         total += 3 * rtdd_round_up((size_t)L.pitchB * L.rows, 256);
+        total += rtdd_round_up((size_t)8 * RTDD_MAX_HALO * L.pitchF * sizeof(float), 256);     // staged peer exchange (rtdd_strip_push)
     }
     e = cudaMalloc(&ctx->arena, total);
     if (e != cudaSuccess) { cudaStreamDestroy(ctx->captureStream); cudaStreamDestroy(ctx->ownStream); delete ctx; return (int)e; }
@@ -373,6 +374,7 @@ int rtdd_create(int rows, int cols, int levels, int device, rtdd_ctx **out)
         L.linkR = (uint8_t *)p; p += rtdd_round_up((size_t)L.pitchB * L.rows, 256);
         L.linkD = (uint8_t *)p; p += rtdd_round_up((size_t)L.pitchB * L.rows, 256);
         L.mask = (uint8_t *)p;  p += rtdd_round_up((size_t)L.pitchB * L.rows, 256);
+        L.stage = (float *)p;   p += rtdd_round_up((size_t)8 * RTDD_MAX_HALO * L.pitchF * sizeof(float), 256);
     }
     build_tensor_maps(ctx);
     for (int l = 0; l < levels && e == cudaSuccess; l++) {
@@ -467,6 +469,10 @@ int rtdd_set_tuning(rtdd_ctx *ctx, const char *key, int value)
         DeviceGuard guard(ctx->device);
         cudaStreamSynchronize(ctx->stream);
         destroy_graphs(ctx);
+        return 0;
+    }
+    if (strcmp(key, "strip_peer_staging") == 0 && (value == 0 || value == 1)) {
+        ctx->peerStaging = (value != 0);
         return 0;
     }
     if (strcmp(key, "resident_two_sweep") == 0 && (value == 0 || value == 1)) {
@@ -708,8 +714,83 @@ int rtdd_strip_neighbours(rtdd_ctx *ctx, int level, int ownBegin, int ownEnd, in
         return rtdd_fail(ctx, RTDD_E_ARG, "rtdd_strip_neighbours");
     L.stripOwnBegin = ownBegin; L.stripOwnEnd = ownEnd; L.stripHalo = halo;
     L.stripUpWinBegin = aboveWinBegin; L.stripDnWinBegin = belowWinBegin;
-    L.stripFused = true;
+    L.stripFused = !ctx->peerStaging;      // staged exchange: the passes stay the plain kernels
     L.stripPushOff = false;
+    if (ctx->peerStaging && halo > RTDD_MAX_HALO) return rtdd_fail(ctx, RTDD_E_ARG, "rtdd_strip_neighbours (halo beyond the staging area)");
+    return 0;
+}
+
+// ---- staged peer exchange -------------------------------------------------------------------------
+// staging rows of level L: [buffer][side: 0 = rows from the rank above, 1 = from the rank below][plane: x_k, x_{k-1}]
+static float *stage_rows(const RtddLevel &L, char *arenaBase, const rtdd_ctx *ctx, int buffer, int side, int plane)
+{
+    const size_t off = (char *)L.stage - (char *)ctx->arena;
+    return (float *)(arenaBase + off) + (size_t)((buffer * 2 + side) * 2 + plane) * RTDD_MAX_HALO * L.pitchF;
+}
+
+int rtdd_strip_push(rtdd_ctx *ctx, int level)
+{
+    if (!ctx) return RTDD_E_ARG;
+    if (level < 0 || level >= ctx->levels) return rtdd_fail(ctx, RTDD_E_ARG, "rtdd_strip_push");
+    RtddLevel &L = ctx->lv[level];
+    if (!ctx->peerStaging || L.stripRows <= 0 || L.stripHalo < 1) return rtdd_fail(ctx, RTDD_E_STATE, "rtdd_strip_push (rtdd_strip_neighbours with staging not called)");
+    DeviceGuard guard(ctx->device);
+    const int H = L.stripHalo;
+    const int gt = L.stripOwnBegin - L.stripBegin;
+    const int own1 = gt + (L.stripOwnEnd - L.stripOwnBegin);
+    const int buffer = (int)(L.peerSeq & 1u);
+    const float *xk = L.x[L.stripPair], *xp = L.x[L.stripPair + 1];
+    const size_t offW = (char *)L.dStripWords - (char *)ctx->arena;
+    rtdd::HaloRows up = {}, dn = {};
+    unsigned int *upFlag = nullptr, *dnFlag = nullptr;
+    if (ctx->peerUp && L.stripUpWinBegin >= 0) {       // my first H own rows are the rank above's "rows from below"
+        up.srcX = xk + (size_t)gt * L.pitchF; up.srcP = xp + (size_t)gt * L.pitchF;
+        up.dstX = stage_rows(L, ctx->peerUp, ctx, buffer, 1, 0); up.dstP = stage_rows(L, ctx->peerUp, ctx, buffer, 1, 1);
+        up.rows = H;
+        upFlag = (unsigned int *)(ctx->peerUp + offW) + 6;
+    }
+    if (ctx->peerDn && L.stripDnWinBegin >= 0) {       // my last H own rows are the rank below's "rows from above"
+        dn.srcX = xk + (size_t)(own1 - H) * L.pitchF; dn.srcP = xp + (size_t)(own1 - H) * L.pitchF;
+        dn.dstX = stage_rows(L, ctx->peerDn, ctx, buffer, 0, 0); dn.dstP = stage_rows(L, ctx->peerDn, ctx, buffer, 0, 1);
+        dn.rows = H;
+        dnFlag = (unsigned int *)(ctx->peerDn + offW) + 5;
+    }
+    RTDD_TRY(rtdd::launch_halo_push(ctx->stream, up, dn, L.pitchF, L.dStripWords + 4, upFlag, dnFlag, L.peerSeq + 1u), "rtdd_strip_push");
+    ctx->launches++;
+    return 0;
+}
+
+int rtdd_strip_pull(rtdd_ctx *ctx, int level)
+{
+    if (!ctx) return RTDD_E_ARG;
+    if (level < 0 || level >= ctx->levels) return rtdd_fail(ctx, RTDD_E_ARG, "rtdd_strip_pull");
+    RtddLevel &L = ctx->lv[level];
+    if (!ctx->peerStaging || L.stripRows <= 0 || L.stripHalo < 1) return rtdd_fail(ctx, RTDD_E_STATE, "rtdd_strip_pull (rtdd_strip_neighbours with staging not called)");
+    DeviceGuard guard(ctx->device);
+    const int H = L.stripHalo;
+    const int gt = L.stripOwnBegin - L.stripBegin;
+    const int own1 = gt + (L.stripOwnEnd - L.stripOwnBegin);
+    const int buffer = (int)(L.peerSeq & 1u);
+    float *xk = L.x[L.stripPair], *xp = L.x[L.stripPair + 1];
+    rtdd::HaloRows up = {}, dn = {};
+    const unsigned int *waitUp = nullptr, *waitDn = nullptr;
+    if (ctx->peerUp && L.stripUpWinBegin >= 0) {       // rows from the rank above -> my upper ghost rows
+        if (gt != H) return rtdd_fail(ctx, RTDD_E_STATE, "rtdd_strip_pull (upper ghost rows != halo)");
+        up.srcX = stage_rows(L, (char *)ctx->arena, ctx, buffer, 0, 0); up.srcP = stage_rows(L, (char *)ctx->arena, ctx, buffer, 0, 1);
+        up.dstX = xk; up.dstP = xp;
+        up.rows = H;
+        waitUp = L.dStripWords + 5;
+    }
+    if (ctx->peerDn && L.stripDnWinBegin >= 0) {       // rows from the rank below -> my lower ghost rows
+        if (own1 + H != L.stripRows) return rtdd_fail(ctx, RTDD_E_STATE, "rtdd_strip_pull (lower ghost rows != halo)");
+        dn.srcX = stage_rows(L, (char *)ctx->arena, ctx, buffer, 1, 0); dn.srcP = stage_rows(L, (char *)ctx->arena, ctx, buffer, 1, 1);
+        dn.dstX = xk + (size_t)own1 * L.pitchF; dn.dstP = xp + (size_t)own1 * L.pitchF;
+        dn.rows = H;
+        waitDn = L.dStripWords + 6;
+    }
+    RTDD_TRY(rtdd::launch_halo_pull(ctx->stream, up, dn, L.pitchF, waitUp, waitDn, L.peerSeq + 1u), "rtdd_strip_pull");
+    L.peerSeq++;
+    ctx->launches++;
     return 0;
 }
 

@@ -37,7 +37,11 @@ struct RtddLevel {
     bool stripFused = false, stripPushOff = false;
     int stripOwnBegin = 0, stripOwnEnd = 0, stripHalo = 0, stripUpWinBegin = -1, stripDnWinBegin = -1;
     unsigned int stripPassAbs = 0, stripFirstPassAbs = 0, stripCtaAbs = 0;   // monotonically increasing tickets
-    unsigned int *dStripWords = nullptr;   // [0] CTA ticket, [1] flag written by the rank above, [2] flag written by the rank below
+    unsigned int *dStripWords = nullptr;   // [0] CTA ticket, [1] flag written by the rank above, [2] flag written by the rank below;
+                                           // staged exchange: [4] push-kernel ticket, [5] sequence pushed by the rank above, [6] ... below
+    // staged peer exchange (rtdd_strip_push / rtdd_strip_pull): [buffer 2][from above, from below][x_k, x_{k-1}][RTDD_MAX_HALO rows]
+    float *stage = nullptr;
+    unsigned int peerSeq = 0;              // exchanges done so far on this level (monotonic; identical on every rank)
     unsigned int *dResidual = nullptr;   // bits of the max-norm of the last sweep's update (rtdd_level_residual)
 };
 
@@ -96,6 +100,7 @@ struct rtdd_ctx {
     uint8_t *bgr = nullptr; size_t bgrPitch = 0;
     uint8_t *depthU8 = nullptr; size_t depthU8Pitch = 0;
     bool imageSet = false;
+    bool peerStaging = false;          // rtdd_set_tuning("strip_peer_staging", 1): halo rows travel through rtdd_strip_push / _pull
     bool frameSatValid = false;        // satScratch holds the summed-area table of the frame image (rtdd_frame_effects)
     // defocus scratch (summed-area tables), grown on demand
     void *satScratch = nullptr; size_t satBytes = 0;
@@ -143,10 +148,21 @@ cudaError_t launch_sweep_single(cudaStream_t s, const RtddLevel &L, const float 
                                 float *out, float omega, float gamma, bool firstSweep, const SweepTarget *target = nullptr);
 // temporally blocked: T sweeps (x, prev) -> (xOut, prevOut); omegas passed by value (<= RTDD_MAX_T)
 #define RTDD_MAX_T 16
+#define RTDD_MAX_HALO 32      // ghost rows per open strip side the staged peer exchange can carry
 struct OmegaPack { float w[RTDD_MAX_T]; };
 cudaError_t launch_sweep_blocked(cudaStream_t s, const RtddLevel &L, const float *lut, const float *x, const float *prev,
                                  float *xOut, float *prevOut, OmegaPack om, int T, int nsweeps, float gamma, bool firstSweep, int smCount,
                                  const SweepTarget *target = nullptr, struct HaloPush *push = nullptr);
+// staged peer exchange: rows of (x_k, x_{k-1}) between this rank's planes and a staging area, plus the completion flags
+struct HaloRows {
+    const float *srcX, *srcP;     // first row to copy of each plane (null: nothing on this side)
+    float *dstX, *dstP;
+    int rows;
+};
+cudaError_t launch_halo_push(cudaStream_t s, HaloRows up, HaloRows dn, int pitchF, unsigned int *ticket,
+                             unsigned int *upFlag, unsigned int *dnFlag, unsigned int flagValue);
+cudaError_t launch_halo_pull(cudaStream_t s, HaloRows up, HaloRows dn, int pitchF, const unsigned int *waitUp, const unsigned int *waitDn,
+                             unsigned int value);
 cudaError_t launch_halo_wait(cudaStream_t s, const unsigned int *waitUp, const unsigned int *waitDn, unsigned int value);
 int blocked_max_T();
 void set_blocked_tile_override(int tile);

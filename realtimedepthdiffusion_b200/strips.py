@@ -71,9 +71,10 @@ def _solve_split_level(engine, l, rank, nranks, strips_l, iters, halo, pass_swee
     a, b = strips_l[rank]
     w0, w1 = max(0, a - halo), min(rows, b + halo)
     engine.strip_init(l, w0, w1)
-    fused = bool(getattr(engine, "fused_halo", False))
+    staged = bool(getattr(engine, "staged_halo", False))      # peer memory through staging rows (rtdd_strip_push / _pull)
+    fused = bool(getattr(engine, "fused_halo", False)) and not staged
     T = halo if (pass_sweeps is None or fused) else max(1, min(int(pass_sweeps), halo))   # the fused push is per pass
-    if fused:
+    if fused or staged:
         # the sweep passes push their boundary rows into the neighbours' ghost rows themselves (peer memory)
         up0 = max(0, strips_l[rank - 1][0] - halo) if rank > 0 else -1
         dn0 = max(0, strips_l[rank + 1][0] - halo) if rank < nranks - 1 else -1
@@ -93,6 +94,12 @@ def _solve_split_level(engine, l, rank, nranks, strips_l, iters, halo, pass_swee
             since = 0
             yield Exchange(l, None, None, None, None)     # no data: only keeps single-process emulations in lockstep
         elif (since >= halo or k >= iters) and (k < iters or l > 0):   # the last exchange feeds the prolongation
+            if staged:
+                engine.strip_push(l)                      # boundary rows -> the neighbours' staging rows + flags
+                since = 0
+                yield Exchange(l, None, None, None, None) # (single-process emulations: everybody pushes before anybody pulls)
+                engine.strip_pull(l)                      # wait for the neighbours' flags, staging rows -> my ghost rows
+                continue
             xk, xkm1 = engine.strip_planes(l)
             gt, gb = a - w0, w1 - b                       # ghost rows above / below
             own0, own1 = gt, gt + (b - a)
@@ -264,6 +271,7 @@ class GpuStripEngine:
         self.depth_u8 = pitched_empty(rows, cols, torch.uint8, self.dev, fill=0)
         self._views = {}
         self.fused_halo = False      # set by set_peers / enable_fused_halo_distributed
+        self.staged_halo = False     # set by enable_staged_halo
         self.marks = None            # set to [] to collect (label, event) pairs for one frame
 
     # -- helpers ------------------------------------------------------------------
@@ -366,6 +374,19 @@ class GpuStripEngine:
     def strip_neighbours(self, l, a, b, halo, up0, dn0):
         from ._native import lib
         self._ck(lib.rtdd_strip_neighbours(self.ctx._h, l, int(a), int(b), int(halo), int(up0), int(dn0)))
+
+    def strip_push(self, l):
+        from ._native import lib
+        self._ck(lib.rtdd_strip_push(self.ctx._h, l))
+
+    def strip_pull(self, l):
+        from ._native import lib
+        self._ck(lib.rtdd_strip_pull(self.ctx._h, l))
+
+    def enable_staged_halo(self):
+        """After set_peers / enable_fused_halo_*: keep the plain sweep kernels and move halo rows with push / pull kernels."""
+        self.ctx.set_tuning("strip_peer_staging", 1)
+        self.staged_halo = True
 
     def strip_wait(self, l):
         from ._native import lib

@@ -597,7 +597,7 @@ def test_full_size_variants_agree_and_dirichlet_holds(rtdd, rows, cols):
 
 # ---- row strips (multi-GPU domain decomposition), emulated on one GPU --------------------------------
 
-@pytest.mark.parametrize("fused,pass_sweeps", [(False, None), (True, None), (False, 8)])
+@pytest.mark.parametrize("fused,pass_sweeps", [(False, None), (True, None), (False, 8), ("staged", None), ("staged", 8)])
 @pytest.mark.parametrize("rows,cols,nranks,halo,iters", [(512, 640, 2, 8, 150), (700, 333, 3, 8, 90), (1080, 1920, 4, 8, 1000), (401, 260, 2, 5, 64)])
 def test_strip_decomposition_on_one_gpu_is_bit_identical(rtdd, rows, cols, nranks, halo, iters, fused, pass_sweeps):
     """Several ranks' worth of strip contexts on ONE device, driven in lockstep with device-to-device halo copies:
@@ -617,6 +617,10 @@ def test_strip_decomposition_on_one_gpu_is_bit_identical(rtdd, rows, cols, nrank
         # the sweep passes write the neighbours' ghost rows themselves (here: plain device pointers of the same process;
         # the passes run one after the other on one device, so the in-kernel flag waits are already satisfied)
         strips.enable_fused_halo_local(engines)
+        if fused == "staged":
+            # plain sweep kernels; the halo rows go through the neighbours' staging rows (rtdd_strip_push / _pull)
+            for e in engines:
+                e.enable_staged_halo()
     if pass_sweeps:
         halo = 2 * pass_sweeps                  # two passes of `pass_sweeps` sweeps between exchanges, twice the ghost rows
     results, exchanges = strips.run_local(engines, iters, halo=halo, min_strip_pixels=1, pass_sweeps=pass_sweeps)

@@ -80,6 +80,7 @@ def main():
     ap.add_argument("--min-strip-pixels", type=int, default=1 << 22)
     ap.add_argument("--check", action="store_true")
     ap.add_argument("--fused", action="store_true", help="halo rows pushed by the sweep kernels over peer memory instead of NCCL send/recv")
+    ap.add_argument("--staged", action="store_true", help="peer memory through staging rows: plain sweep kernels + small push / pull kernels (no NCCL on the data path)")
     ap.add_argument("--level0-sweeps", type=int, default=0,
                     help="SURVEY.md 8d config 5 (i): time only this many finest-level sweeps (strip-decomposed) instead of the whole pyramid")
     args = ap.parse_args()
@@ -96,8 +97,10 @@ def main():
     with torch.cuda.stream(stream):
         bgr, scribble, edited = synth_on_device(rows, cols, 1005, ctx)
         eng = strips.GpuStripEngine(ctx, bgr, scribble, edited)
-        if args.fused and world > 1:
+        if (args.fused or args.staged) and world > 1:
             eng.enable_fused_halo_distributed(dist)
+            if args.staged:
+                eng.enable_staged_halo()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = args.level0_sweeps
         ps = args.pass_sweeps or None
@@ -179,7 +182,7 @@ def main():
             per.append({"level": l, "size": "%dx%d" % (c, r), "sweeps": it, "split": plan[l] is not None})
         print(json.dumps({"workload": "configs[4]%s: %dx%d single synthetic image, row strips + NVLink halo exchange (%s), halo %d rows%s"
                                       % (" (i) finest level only, %d sweeps incl. edge-weight pass and result copy" % l0 if l0 > 0 else "",
-                                         cols, rows, "peer-memory stores + flags" if args.fused else "NCCL send/recv", args.halo, (", FUSED: halo rows pushed by the sweep kernels over peer memory" if args.fused else "")
+                                         cols, rows, "peer-memory staging rows + flags" if args.staged else "peer-memory stores + flags" if args.fused else "NCCL send/recv", args.halo, (", FUSED: halo rows pushed by the sweep kernels over peer memory" if args.fused else "")
                                          + (", passes of %d sweeps" % ps if ps else "")),
                           "n_gpus": world, "ms_per_solve": float(t.item()), "Mpixel-sweeps/s": total / (float(t.item()) * 1e-3) / 1e6,
                           "pixel_sweeps": total, "halo_exchanges_per_solve": exchanges, "levels": per, "scaling": "strong",
