@@ -115,14 +115,14 @@ def _solve_split_level(engine, l, rank, nranks, strips_l, iters, halo, pass_swee
         engine.strip_finish(l, a, b)                      # finest level: ghosts are stale and not needed
 
 
-def level0_coroutine(engine, rank, nranks, sweeps, halo=8, pass_sweeps=None):
+def level0_coroutine(engine, rank, nranks, sweeps, halo=8, pass_sweeps=None, force_strip_path=False):
     """BASELINE configs[4], measurement (i) of SURVEY.md section 8d: only the finest level, a fixed number of sweeps from
     whatever guess engine.depth[0] holds, cut into `nranks` equal row strips (one rank: the ordinary level solve).
     Same per-pixel recipe and the same halo logic as the frame, so owned rows are bit-identical to one GPU."""
     rows = engine.sizes[0][0]
     mark = getattr(engine, "mark", lambda label: None)
     mark("begin")
-    if nranks <= 1:
+    if nranks <= 1 and not force_strip_path:          # (force_strip_path: one rank through rtdd_strip_* with the whole image as its window)
         engine.solve_full(0, sweeps)
         mark("solve L0")
         return [None] * len(engine.sizes), (0, rows)
@@ -210,11 +210,11 @@ def enable_fused_halo_local(engines):
         e.set_peers(bases[r - 1] if r > 0 else None, bases[r + 1] if r + 1 < len(engines) else None)
 
 
-def run_local(engines, max_iterations, halo=8, min_strip_pixels=1 << 22, level0_sweeps=0, pass_sweeps=None):
+def run_local(engines, max_iterations, halo=8, min_strip_pixels=1 << 22, level0_sweeps=0, pass_sweeps=None, force_strip_path=False):
     """All ranks in one process, in lockstep (emulation on one device / CPU unit tests)."""
     n = len(engines)
     if level0_sweeps > 0:
-        cos = [level0_coroutine(e, r, n, level0_sweeps, halo, pass_sweeps) for r, e in enumerate(engines)]
+        cos = [level0_coroutine(e, r, n, level0_sweeps, halo, pass_sweeps, force_strip_path) for r, e in enumerate(engines)]
     else:
         cos = [frame_coroutine(e, r, n, max_iterations, halo, min_strip_pixels, pass_sweeps=pass_sweeps) for r, e in enumerate(engines)]
     results = [None] * n

@@ -82,6 +82,10 @@ def test_level0_only_strips_match_the_single_level_solve(rows, cols, nranks, hal
     solo.st.depth[0] = guess.copy()
     (res, ex0) = strips.run_local([solo], 0, halo=halo, level0_sweeps=sweeps)
     assert ex0 == 0 and res[0][1] == (0, rows)
+    forced = CpuStripEngine(bgr, scribble, edited)              # one rank through the strip entry points, whole image as window
+    forced.st.depth[0] = guess.copy()
+    strips.run_local([forced], 0, halo=halo, level0_sweeps=sweeps, force_strip_path=True)
+    assert np.array_equal(forced.st.depth[0].view(np.uint32), solo.st.depth[0].view(np.uint32))
     engines = [CpuStripEngine(bgr, scribble, edited) for _ in range(nranks)]
     for e in engines:
         e.st.depth[0] = guess.copy()

@@ -81,6 +81,7 @@ def main():
     ap.add_argument("--check", action="store_true")
     ap.add_argument("--fused", action="store_true", help="halo rows pushed by the sweep kernels over peer memory instead of NCCL send/recv")
     ap.add_argument("--staged", action="store_true", help="peer memory through staging rows: plain sweep kernels + small push / pull kernels (no NCCL on the data path)")
+    ap.add_argument("--force-strip-path", action="store_true", help="one GPU, --level0-sweeps: go through rtdd_strip_* with the whole image as the window (isolates the strip path's own overhead)")
     ap.add_argument("--level0-sweeps", type=int, default=0,
                     help="SURVEY.md 8d config 5 (i): time only this many finest-level sweeps (strip-decomposed) instead of the whole pyramid")
     args = ap.parse_args()
@@ -134,7 +135,8 @@ def main():
             if world > 1:
                 plan, own, exchanges = strips.run_distributed(eng, dist, 1000, halo=args.halo, min_strip_pixels=args.min_strip_pixels, level0_sweeps=l0, pass_sweeps=ps)
             else:
-                res, exchanges = strips.run_local([eng], 1000, halo=args.halo, min_strip_pixels=args.min_strip_pixels, level0_sweeps=l0, pass_sweeps=ps)
+                res, exchanges = strips.run_local([eng], 1000, halo=args.halo, min_strip_pixels=args.min_strip_pixels, level0_sweeps=l0, pass_sweeps=ps,
+                                                  force_strip_path=args.force_strip_path)
                 plan, own = res[0]
             ev1.record(stream)
             torch.cuda.synchronize()
