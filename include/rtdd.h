@@ -126,7 +126,11 @@ int rtdd_set_sweep_variant(rtdd_ctx *ctx, int variant, int sweepsPerPass);
  * "blocked_tma": 1 (default) TMA-fed persistent form of the 128x64 kernel, 0 = plain LDG form;
  * "resident_two_sweep": 1 = two sweeps per neighbour exchange in the cluster-resident kernel, 0 (default) = one;
  * "resident_warps": target warps per CTA of the cluster-resident kernel (default 8);
- * "pdl": 1 (default) sweep passes are chained with programmatic dependent launch, 0 = plain stream order. */
+ * "pdl": 1 (default) sweep passes are chained with programmatic dependent launch, 0 = plain stream order;
+ * "strip_residual": 1 = rtdd_strip_pass also fills the level's residual word (rtdd_level_residual), default 0;
+ * "strip_peer_staging": 1 = halo rows of a strip level travel through rtdd_strip_push / rtdd_strip_pull, default 0;
+ * "fused_prolong": 1 = whole-frame path forms a level's guess inside its set-up kernel, default 0 (no faster);
+ * "resident_r1_max_warps": largest one-row-per-warp CTA of the cluster-resident kernel (default 32). */
 int rtdd_set_tuning(rtdd_ctx *ctx, const char *key, int value);
 
 /* ---- row strips: one level of one very large image split across GPUs (BASELINE configs[4]) --------

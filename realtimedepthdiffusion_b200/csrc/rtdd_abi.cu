@@ -471,6 +471,10 @@ int rtdd_set_tuning(rtdd_ctx *ctx, const char *key, int value)
         destroy_graphs(ctx);
         return 0;
     }
+    if (strcmp(key, "strip_residual") == 0 && (value == 0 || value == 1)) {
+        ctx->stripResidual = (value != 0);
+        return 0;
+    }
     if (strcmp(key, "strip_peer_staging") == 0 && (value == 0 || value == 1)) {
         ctx->peerStaging = (value != 0);
         return 0;
@@ -599,6 +603,11 @@ int rtdd_solve_level_converge(rtdd_ctx *ctx, float *depth, size_t depthPitch, co
     const int T = 8;
     int done = 0;
     float res = INFINITY;
+    struct ResidualOn {                                       // the passes of this call fill the residual word
+        rtdd_ctx *c; bool old;
+        explicit ResidualOn(rtdd_ctx *x) : c(x), old(x->stripResidual) { c->stripResidual = true; }
+        ~ResidualOn() { c->stripResidual = old; }
+    } residualOn(ctx);
     while (done < maxIterations) {
         int chunk = maxIterations - done < checkEvery ? maxIterations - done : checkEvery;
         while (chunk > 0) {
@@ -831,9 +840,12 @@ int rtdd_strip_pass(rtdd_ctx *ctx, int level, int firstSweep, int nsweeps, int h
     RtddLevel W = L;
     W.rows = L.stripRows;
     const int src = L.stripPair, dst = src ^ 2;
-    // the residual of this pass's last sweep (over the whole window; stale ghost rows can only raise it)
-    const rtdd::SweepTarget tgt = {nullptr, 0, nullptr, 0, L.dResidual};
-    RTDD_TRY(cudaMemsetAsync(L.dResidual, 0, sizeof(unsigned int), ctx->stream), "rtdd_strip_pass");
+    // on request, the residual of this pass's last sweep (over the whole window; stale ghost rows can only raise it).  Not by
+    // default: measured on the 16K level-0 pass, accumulating it costs 4.14 vs 3.87 ms per pass (ncu launch lists,
+    // profiles/r01_strip_path_vs_level_graph.txt)
+    const bool wantResidual = ctx->stripResidual;
+    const rtdd::SweepTarget tgt = {nullptr, 0, nullptr, 0, wantResidual ? L.dResidual : nullptr};
+    if (wantResidual) RTDD_TRY(cudaMemsetAsync(L.dResidual, 0, sizeof(unsigned int), ctx->stream), "rtdd_strip_pass");
     rtdd::HaloPush hp = {};
     bool fused = L.stripFused && (ctx->peerUp || ctx->peerDn);
     // a pass that neither waits for nor feeds a neighbour (the finest level's only pass) runs the plain kernel

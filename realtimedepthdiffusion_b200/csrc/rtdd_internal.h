@@ -100,6 +100,7 @@ struct rtdd_ctx {
     uint8_t *bgr = nullptr; size_t bgrPitch = 0;
     uint8_t *depthU8 = nullptr; size_t depthU8Pitch = 0;
     bool imageSet = false;
+    bool stripResidual = false;        // rtdd_strip_pass also fills the level's residual word (+7 % per pass at 16K: only rtdd_solve_level_converge asks)
     bool peerStaging = false;          // rtdd_set_tuning("strip_peer_staging", 1): halo rows travel through rtdd_strip_push / _pull
     bool frameSatValid = false;        // satScratch holds the summed-area table of the frame image (rtdd_frame_effects)
     // defocus scratch (summed-area tables), grown on demand
