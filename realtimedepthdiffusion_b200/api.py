@@ -47,6 +47,17 @@ def pitched_empty(rows, cols, dtype, device, channels=1, align=512, fill=None):
     return base[:, : cols * channels]
 
 
+def to_dev(a, channels=1, device="cuda"):
+    """numpy [rows, cols(, channels)] -> pitched device plane [rows, cols * channels] (tools, tests)."""
+    import numpy as np
+    a = np.ascontiguousarray(a)
+    rows, cols = a.shape[:2]
+    dt = torch.from_numpy(a.reshape(rows, -1))
+    out = pitched_empty(rows, cols, dt.dtype, device, channels=channels)
+    out.copy_(dt)
+    return out
+
+
 def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 

@@ -1,6 +1,6 @@
 """CPU tests of the oracle itself: known answers from SURVEY.md Appendix A, the OpenCV
 restatements against cv2, and the golden vectors recorded from the reference's own kernels
-on a B200 (tests/golden/ref_*.npz, tools/gen_golden_ref.py)."""
+on a B200 (tests/golden/ref_*.npz, tests/golden/gen_golden_ref.py)."""
 import glob
 import hashlib
 import os
@@ -137,7 +137,7 @@ def test_defocus_kernel_size_table():
 def _golden(pattern):
     files = sorted(glob.glob(os.path.join(GOLD, pattern)))
     if not files:
-        pytest.skip("no golden vectors %s (generate with tools/gen_golden_ref.py on a GPU box)" % pattern)
+        pytest.skip("no golden vectors %s (generate with tests/golden/gen_golden_ref.py on a GPU box)" % pattern)
     return files
 
 

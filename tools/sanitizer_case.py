@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import realtimedepthdiffusion_b200 as rtdd          # noqa: E402
 from realtimedepthdiffusion_b200 import strips, synth       # noqa: E402
-from oracle.mainloop import to_dev                  # noqa: E402
+from realtimedepthdiffusion_b200.api import to_dev   # noqa: E402
 
 rows, cols = 203, 317
 bgr, scribble, edited = synth.synth_case(rows, cols, 5)

@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import realtimedepthdiffusion_b200 as rtdd          # noqa: E402
 from realtimedepthdiffusion_b200 import synth       # noqa: E402
-from oracle.mainloop import to_dev                  # noqa: E402
+from realtimedepthdiffusion_b200.api import to_dev   # noqa: E402
 
 LEVELS = [(2160, 3840, 31), (1080, 1920, 62), (540, 960, 125), (270, 480, 250), (135, 240, 500)]
 if len(sys.argv) > 1:

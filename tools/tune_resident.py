@@ -8,7 +8,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import realtimedepthdiffusion_b200 as rtdd          # noqa: E402
 from realtimedepthdiffusion_b200 import synth       # noqa: E402
-from oracle.mainloop import to_dev                  # noqa: E402
+from realtimedepthdiffusion_b200.api import to_dev   # noqa: E402
 
 for rows, cols, iters in ((67, 120, 1000), (135, 240, 500), (64, 64, 1000), (128, 128, 500), (256, 256, 250)):
     rng = np.random.default_rng(1)
