@@ -1,7 +1,7 @@
 // Drop-in replacement for the reference's include/GPUSolver.h (signatures at
 // /root/reference/include/GPUSolver.h:6-10).  Same four free functions with C++
 // linkage, same argument meaning, same "void, print the CUDA error, carry on"
-// convention; implemented in realtimedepthdiffusion_b200/csrc/shims.cpp on top
+// convention; implemented in realtimedepthdiffusion_b200/csrc/gpu_shims.cpp on top
 // of the C ABI declared in include/rtdd.h.
 #ifndef GPU_SOLVER_H
 #define GPU_SOLVER_H
