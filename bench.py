@@ -439,8 +439,18 @@ def main():
     ap.add_argument("--seed-offset", type=int, default=0, help="extra offset on the synthetic image seed (diagnostics)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    # stdout carries exactly ONE line, the JSON result: anything libraries print there meanwhile (NCCL's version banner
+    # under NCCL_DEBUG=VERSION, for one) is sent to stderr instead
+    sys.stdout.flush()
+    result_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.write(result_fd, (json.dumps(obj) + "\n").encode())
+
     if not torch.cuda.is_available():
-        print(json.dumps({"error": "no CUDA device: bench.py measures the CUDA path only (no CPU fallback)"}))
+        emit({"error": "no CUDA device: bench.py measures the CUDA path only (no CPU fallback)"})
         sys.exit(2)
     if args.impl == "reference":
         # rank 0 alone runs the reference arm; the other ranks exit 0 without work (no process group needed)
@@ -458,7 +468,7 @@ def main():
             rows, cols, _ = WORKLOADS[args.workload]
             from realtimedepthdiffusion_b200 import pyramid_levels
             line["cpu_baseline"] = cpu_baseline(rows, cols, pyramid_levels(rows, cols))
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
