@@ -111,6 +111,20 @@ rows, cols, iters, halo = 203, 150, 70, 4
 bgr, scribble, edited = synth.synth_case(rows, cols, 321)
 eng = CpuStripEngine(bgr, scribble, edited)
 plan, own, exchanges = strips.run_distributed(eng, dist, iters, halo=halo, min_strip_pixels=1)
+# the same frame with twice the ghost rows and two passes per exchange, and the finest level alone: same rows, fewer exchanges
+eng2 = CpuStripEngine(bgr, scribble, edited)
+plan2, own2, exchanges2 = strips.run_distributed(eng2, dist, iters, halo=2 * halo, min_strip_pixels=1, pass_sweeps=halo)
+same2 = own2 == own and exchanges2 < exchanges and np.array_equal(eng2.st.depth[0][own[0]:own[1]].view(np.uint32), eng.st.depth[0][own[0]:own[1]].view(np.uint32))
+eng3 = CpuStripEngine(bgr, scribble, edited)
+guess = np.random.default_rng(3).uniform(0, 255, (rows, cols)).astype(np.float32)
+eng3.st.depth[0] = guess.copy()
+plan3, own3, exchanges3 = strips.run_distributed(eng3, dist, 0, halo=halo, level0_sweeps=9)
+solo = CpuStripEngine(bgr, scribble, edited)
+solo.st.depth[0] = guess.copy()
+strips.run_local([solo], 0, halo=halo, level0_sweeps=9)
+same3 = exchanges3 == 2 and np.array_equal(eng3.st.depth[0][own3[0]:own3[1]].view(np.uint32), solo.st.depth[0][own3[0]:own3[1]].view(np.uint32))
+flag = torch.tensor([1 if (same2 and same3) else 0])
+dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 full = torch.zeros((rows, cols), dtype=torch.float32)
 full[own[0]:own[1]] = torch.from_numpy(eng.st.depth[0][own[0]:own[1]])
 dist.all_reduce(full)                      # disjoint rows: the sum assembles the image
@@ -118,7 +132,7 @@ if rank == 0:
     st = ob.FrameState(bgr)
     st.solve(scribble, edited, iters)
     ok = np.array_equal(full.numpy().view(np.uint32), st.depth[0].view(np.uint32))
-    print("STRIPS_OK" if ok and exchanges > 0 else "STRIPS_MISMATCH", exchanges, flush=True)
+    print("STRIPS_OK" if ok and exchanges > 0 and int(flag.item()) == 1 else "STRIPS_MISMATCH", exchanges, exchanges2, exchanges3, int(flag.item()), flush=True)
 dist.destroy_process_group()
 '''
 
