@@ -142,6 +142,14 @@ int rtdd_set_tuning(rtdd_ctx *ctx, const char *key, int value);
  * must be refreshed from the neighbouring rank before the next pass: rtdd_strip_planes returns the device
  * planes holding x_k and x_{k-1} (row 0 = winBegin, row pitch pitchBytes) to send from / receive into;
  * rtdd_strip_finish copies final rows [rowBegin, rowEnd) (level coordinates) into the pitched depth plane. */
+/* Host-side planning of the decomposition (no device work).  rtdd_plan_strips: levels are finest first; for every split
+ * level l, split[l] = 1 and rank r owns rows [ownBegin[l * nranks + r], ownEnd[l * nranks + r]); the coarsest split level
+ * is cut evenly and every finer one doubles its boundaries.  rtdd_strip_schedule: the passes of one split level and the
+ * halo exchanges between them (several passes of passSweeps <= halo sweeps may share one exchange); returns the number
+ * of passes, negative on error. */
+int rtdd_plan_strips(const int *levelRows, const int *levelCols, int levels, int nranks, int halo, long long minStripPixels,
+                     int *split, int *ownBegin, int *ownEnd);
+int rtdd_strip_schedule(int iters, int halo, int passSweeps, int level, int *sweepsOfPass, int *exchangeAfter, int capacity);
 int rtdd_strip_init(rtdd_ctx *ctx, int level, const float *depth, size_t depthPitch, const uint8_t *scribble, size_t scribblePitch,
                     const uint8_t *gray, size_t grayPitch, int rows, int cols, int winBegin, int winEnd);
 int rtdd_strip_pass(rtdd_ctx *ctx, int level, int firstSweep, int nsweeps, int haloT);

@@ -48,6 +48,8 @@ SIGNATURES = {
     "rtdd_strip_set_peers": (i32, [vp, vp, vp]),
     "rtdd_strip_neighbours": (i32, [vp, i32, i32, i32, i32, i32, i32]),
     "rtdd_strip_wait": (i32, [vp, i32]),
+    "rtdd_plan_strips": (i32, [vp, vp, i32, i32, i32, C.c_longlong, vp, vp, vp]),
+    "rtdd_strip_schedule": (i32, [i32, i32, i32, i32, vp, vp, i32]),
     "rtdd_strip_push": (i32, [vp, i32]),
     "rtdd_strip_pull": (i32, [vp, i32]),
     "rtdd_strip_push_enable": (i32, [vp, i32, i32]),

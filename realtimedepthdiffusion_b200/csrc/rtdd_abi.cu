@@ -318,6 +318,66 @@ int rtdd_level_iterations(int maxIterations, int levels, int level)
     return (int)((float)maxIterations / powf(2.0f, (float)((levels - 1) - level)));
 }
 
+// ---- row-strip planning (host only; no reference counterpart: the reference is single-GPU) -----------------------
+// Which levels are cut into row strips and who owns which rows.  The coarsest level still worth splitting (at least
+// minStripPixels pixels, every strip at least max(halo, 2) rows) is cut evenly; every finer level doubles those
+// boundaries, so a rank's fine rows are exactly the prolongation of its own coarse rows.  Levels coarser than that are
+// replicated (solved by every rank).
+int rtdd_plan_strips(const int *levelRows, const int *levelCols, int levels, int nranks, int halo, long long minStripPixels,
+                     int *split, int *ownBegin, int *ownEnd)
+{
+    if (!levelRows || !levelCols || !split || !ownBegin || !ownEnd || levels < 1 || nranks < 1 || halo < 1) return RTDD_E_ARG;
+    for (int l = 0; l < levels; l++) split[l] = 0;
+    if (nranks <= 1) return 0;
+    int cs = -1;
+    const int minRows = halo > 2 ? halo : 2;
+    for (int l = 0; l < levels; l++) {
+        if ((long long)levelRows[l] * levelCols[l] >= minStripPixels && levelRows[l] / nranks >= minRows) cs = l;
+        else break;
+    }
+    if (cs < 0) return 0;
+    std::vector<long long> bounds(nranks + 1);
+    for (int r = 0; r < nranks; r++) bounds[r] = ((long long)r * levelRows[cs]) / nranks;
+    for (int l = cs; l >= 0; l--) {
+        if (l < cs)
+            for (int r = 0; r < nranks; r++) bounds[r] *= 2;
+        bounds[nranks] = levelRows[l];
+        split[l] = 1;
+        for (int r = 0; r < nranks; r++) {
+            ownBegin[l * nranks + r] = (int)bounds[r];
+            ownEnd[l * nranks + r] = (int)bounds[r + 1];
+            if (bounds[r + 1] - bounds[r] < halo) return RTDD_E_ARG;          // a strip shorter than its halo
+        }
+    }
+    return 0;
+}
+
+// The passes of one split level: `iters` sweeps in passes of at most passSweeps (<= halo) sweeps, with a halo exchange
+// whenever `halo` sweeps have gone by since the ghost rows were last fresh, and after the last pass if the level feeds a
+// prolongation (level > 0).  Fills sweepsOfPass[i] and exchangeAfter[i]; returns the number of passes (or a negative
+// RTDD_E_* when `capacity` is too small).
+int rtdd_strip_schedule(int iters, int halo, int passSweeps, int level, int *sweepsOfPass, int *exchangeAfter, int capacity)
+{
+    if (iters < 0 || halo < 1 || level < 0 || !sweepsOfPass || !exchangeAfter) return -RTDD_E_ARG;
+    int T = passSweeps;
+    if (T < 1 || T > halo) T = halo;
+    int k = 0, since = 0, n = 0;
+    while (k < iters) {
+        int m = T;
+        if (iters - k < m) m = iters - k;
+        if (halo - since < m) m = halo - since;
+        if (n >= capacity) return -RTDD_E_ARG;
+        k += m;
+        since += m;
+        const bool exchange = (since >= halo || k >= iters) && (k < iters || level > 0);
+        sweepsOfPass[n] = m;
+        exchangeAfter[n] = exchange ? 1 : 0;
+        if (exchange) since = 0;
+        n++;
+    }
+    return n;
+}
+
 int rtdd_create(int rows, int cols, int levels, int device, rtdd_ctx **out)
 {
     if (!out) return RTDD_E_ARG;

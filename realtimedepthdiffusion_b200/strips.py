@@ -23,30 +23,36 @@ import torch
 def plan_strips(sizes, nranks, halo, min_strip_pixels=1 << 22):
     """sizes: [(rows, cols)] per level, finest first.  Returns plan[level] = None (replicated) or a list of
     (begin, end) owned row ranges per rank.  Strip boundaries double from one level to the next finer one so that
-    a rank's fine rows are the prolongation of its own coarse rows (plus ghosts)."""
+    a rank's fine rows are the prolongation of its own coarse rows (plus ghosts).  The planning itself is the native
+    library's (rtdd_plan_strips, host only)."""
+    from ._native import lib
     levels = len(sizes)
     plan = [None] * levels
     if nranks <= 1:
         return plan
-    # coarsest level that is still worth splitting: big enough and every strip at least `halo` rows tall
-    cs = -1
+    IntArr = C.c_int * levels
+    rows = IntArr(*[int(r) for r, _ in sizes])
+    cols = IntArr(*[int(c) for _, c in sizes])
+    split = IntArr()
+    begin = (C.c_int * (levels * nranks))()
+    end = (C.c_int * (levels * nranks))()
+    rc = lib.rtdd_plan_strips(rows, cols, levels, int(nranks), int(halo), int(min_strip_pixels), split, begin, end)
+    assert rc == 0, "strip shorter than the halo"
     for l in range(levels):
-        rows, cols = sizes[l]
-        if rows * cols >= min_strip_pixels and rows // nranks >= max(halo, 2):
-            cs = l
-        else:
-            break
-    if cs < 0:
-        return plan
-    rows = sizes[cs][0]
-    bounds = [(r * rows) // nranks for r in range(nranks)] + [rows]
-    for l in range(cs, -1, -1):
-        rows = sizes[l][0]
-        if l < cs:
-            bounds = [2 * b for b in bounds[:-1]] + [rows]
-        plan[l] = [(bounds[r], bounds[r + 1]) for r in range(nranks)]
-        assert all(e - b >= halo for b, e in plan[l]), "strip shorter than the halo"
+        if split[l]:
+            plan[l] = [(begin[l * nranks + r], end[l * nranks + r]) for r in range(nranks)]
     return plan
+
+
+def strip_schedule(iters, halo, pass_sweeps, level):
+    """[(sweeps of the pass, exchange after it?)] for one split level (rtdd_strip_schedule, host only)."""
+    from ._native import lib
+    cap = max(int(iters), 1)
+    sweeps = (C.c_int * cap)()
+    exch = (C.c_int * cap)()
+    n = lib.rtdd_strip_schedule(int(iters), int(halo), int(pass_sweeps or 0), int(level), sweeps, exch, cap)
+    assert n >= 0, "rtdd_strip_schedule"
+    return [(sweeps[i], bool(exch[i])) for i in range(n)]
 
 
 def level_iterations(max_iterations, levels, level):
@@ -80,30 +86,24 @@ def _solve_split_level(engine, l, rank, nranks, strips_l, iters, halo, pass_swee
         dn0 = max(0, strips_l[rank + 1][0] - halo) if rank < nranks - 1 else -1
         engine.strip_neighbours(l, a, b, halo, up0, dn0)
     k = 0
-    since = 0                                             # sweeps since the ghost rows were last fresh
-    while k < iters:
-        n = min(T, iters - k, halo - since)
+    for n, exchange in strip_schedule(iters, halo, T, l):
         if fused and l == 0 and k + n >= iters:
             engine.strip_push_enable(l, False)            # the finest level's last pass: nobody reads the ghost rows afterwards
         engine.strip_pass(l, k, n, T)
         k += n
-        since += n
-        if fused:
+        if fused:                                         # (T == halo: the schedule has an exchange after every pass but level 0's last)
             if k >= iters and l > 0:
                 engine.strip_wait(l)                      # ghost rows must be final before the prolongation reads them
-            since = 0
             yield Exchange(l, None, None, None, None)     # no data: only keeps single-process emulations in lockstep
-        elif (since >= halo or k >= iters) and (k < iters or l > 0):   # the last exchange feeds the prolongation
+        elif exchange:                                    # the last exchange of a level > 0 feeds the prolongation
             if staged:
                 engine.strip_push(l)                      # boundary rows -> the neighbours' staging rows + flags
-                since = 0
                 yield Exchange(l, None, None, None, None) # (single-process emulations: everybody pushes before anybody pulls)
                 engine.strip_pull(l)                      # wait for the neighbours' flags, staging rows -> my ghost rows
                 continue
             xk, xkm1 = engine.strip_planes(l)
             gt, gb = a - w0, w1 - b                       # ghost rows above / below
             own0, own1 = gt, gt + (b - a)
-            since = 0
             yield Exchange(l,
                            [xk[own0:own0 + halo], xkm1[own0:own0 + halo]] if gt else None,
                            [xk[0:gt], xkm1[0:gt]] if gt else None,

@@ -37,6 +37,66 @@ def test_plan_strips_geometry():
     assert plan[0][1][0] == 2 * plan[1][1][0] == 4 * plan[2][1][0]
 
 
+def _plan_restated(sizes, nranks, halo, min_strip_pixels):
+    """The planning rule written out in Python, to pin the native rtdd_plan_strips."""
+    levels = len(sizes)
+    plan = [None] * levels
+    cs = -1
+    for l in range(levels):
+        rows, cols = sizes[l]
+        if rows * cols >= min_strip_pixels and rows // nranks >= max(halo, 2):
+            cs = l
+        else:
+            break
+    if nranks <= 1 or cs < 0:
+        return plan
+    bounds = [(r * sizes[cs][0]) // nranks for r in range(nranks)]
+    for l in range(cs, -1, -1):
+        if l < cs:
+            bounds = [2 * b for b in bounds]
+        full = bounds + [sizes[l][0]]
+        plan[l] = [(full[r], full[r + 1]) for r in range(nranks)]
+    return plan
+
+
+def _schedule_restated(iters, halo, pass_sweeps, level):
+    T = halo if not pass_sweeps or pass_sweeps > halo else pass_sweeps
+    out, k, since = [], 0, 0
+    while k < iters:
+        n = min(T, iters - k, halo - since)
+        k += n
+        since += n
+        ex = (since >= halo or k >= iters) and (k < iters or level > 0)
+        out.append((n, ex))
+        if ex:
+            since = 0
+    return out
+
+
+def test_native_planning_matches_its_restatement():
+    rng = np.random.default_rng(11)
+    for _ in range(300):
+        levels = int(rng.integers(1, 9))
+        rows, cols = int(rng.integers(64, 20000)), int(rng.integers(64, 20000))
+        sizes = [(rows >> l, cols >> l) for l in range(levels) if (rows >> l) > 0 and (cols >> l) > 0]
+        nranks, halo = int(rng.integers(1, 9)), int(rng.integers(1, 33))
+        mp = int(rng.choice([1, 1 << 16, 1 << 22]))
+        want = _plan_restated(sizes, nranks, halo, mp)
+        if any(p is not None and any(e - b < halo for b, e in p) for p in want):
+            continue                                       # the native planner refuses strips shorter than the halo
+        assert strips.plan_strips(sizes, nranks, halo, mp) == want
+    for _ in range(300):
+        iters, halo = int(rng.integers(0, 1100)), int(rng.integers(1, 33))
+        ps = int(rng.integers(0, 40))
+        level = int(rng.integers(0, 3))
+        got = strips.strip_schedule(iters, halo, ps, level)
+        assert got == _schedule_restated(iters, halo, ps, level)
+        assert sum(n for n, _ in got) == iters
+    # one exchange per `halo` sweeps; level 0 needs none after its last pass, other levels do
+    assert [e for _, e in strips.strip_schedule(64, 16, 8, 0)] == [False, True, False, True, False, True, False, False]
+    assert [e for _, e in strips.strip_schedule(31, 8, 0, 3)] == [True, True, True, True]
+
+
 @pytest.mark.parametrize("rows,cols,nranks,halo,iters", [(203, 150, 2, 4, 70), (256, 96, 3, 8, 100), (181, 130, 2, 5, 33)])
 def test_lockstep_strips_are_bit_identical_to_the_single_solve(rows, cols, nranks, halo, iters):
     bgr, scribble, edited = synth.synth_case(rows, cols, 321)
