@@ -157,6 +157,62 @@ def test_level0_only_strips_match_the_single_level_solve(rows, cols, nranks, hal
     assert np.array_equal(got.view(np.uint32), solo.st.depth[0].view(np.uint32))
 
 
+class _Recorder:
+    """Engine stand-in that only records which entry points the per-rank frame calls, in order."""
+
+    def __init__(self, sizes, fused, staged):
+        self.sizes, self.fused_halo, self.staged_halo, self.log = sizes, fused, staged, []
+
+    def __getattr__(self, name):
+        if not (name.startswith("strip_") or name in ("annotation_pyramid", "convert_rows", "solve_full", "pyrup_rows", "quantise_rows")):
+            raise AttributeError(name)
+
+        def call(*args):
+            self.log.append((name,) + args)
+        return call
+
+
+@pytest.mark.parametrize("mode", ["fused", "staged"])
+@pytest.mark.parametrize("nranks,halo,pass_sweeps,iters", [(2, 8, None, 150), (4, 16, 8, 1000), (3, 4, None, 33)])
+def test_peer_memory_modes_call_sequence(mode, nranks, halo, pass_sweeps, iters):
+    """The GPU-only exchange modes on the CPU: which rtdd_strip_* calls a rank makes and in which order."""
+    sizes = [(1081 >> l, 700 >> l) for l in range(3)]
+    plan = strips.plan_strips(sizes, nranks, halo, 1)
+    for rank in range(nranks):
+        eng = _Recorder(sizes, True, mode == "staged")
+        co = strips.frame_coroutine(eng, rank, nranks, iters, halo, 1, pass_sweeps=pass_sweeps)
+        yields = 0
+        try:
+            ex = next(co)
+            while True:
+                assert ex.send_up is None and ex.send_dn is None          # no rows travel through the host side
+                eng.log.append(("yield", ex.level))
+                yields += 1
+                ex = co.send(None)
+        except StopIteration:
+            pass
+        names = [c[0] for c in eng.log]
+        for l in range(3):
+            assert plan[l] is not None
+            it = strips.level_iterations(iters, 3, l)
+            sched = strips.strip_schedule(it, halo, halo if mode == "fused" else pass_sweeps, l)
+            calls = [c for c in eng.log if c[0].startswith("strip_") and c[1] == l]
+            passes = [c for c in calls if c[0] == "strip_pass"]
+            assert [c[3] for c in passes] == [n for n, _ in sched] and sum(c[3] for c in passes) == it
+            if mode == "staged":
+                pushes = [i for i, c in enumerate(eng.log) if c[:2] == ("strip_push", l)]
+                assert len(pushes) == sum(1 for _, e in sched if e)
+                for i in pushes:                                            # push, everybody yields, then pull
+                    assert eng.log[i + 1] == ("yield", l) and eng.log[i + 2] == ("strip_pull", l)
+                assert not any(c[0] in ("strip_wait", "strip_push_enable") for c in calls)
+            else:
+                waits = [c for c in calls if c[0] == "strip_wait"]
+                assert len(waits) == (1 if l > 0 else 0)                    # ghost rows final before the prolongation reads them
+                assert ("strip_push_enable", 0, False) in eng.log           # nobody reads level 0's ghost rows after its last pass
+            assert [c[0] for c in calls][:2] == ["strip_init", "strip_neighbours"] and calls[-1][0] == "strip_finish"
+        assert names[-1] == "quantise_rows"
+
+
 WORKER = r'''
 import os, sys
 sys.path.insert(0, %(root)r)
