@@ -124,7 +124,6 @@ int rtdd_set_sweep_variant(rtdd_ctx *ctx, int variant, int sweepsPerPass);
 /* Process-wide tuning knobs for experiments (tools/tune_blocked.py); results never change, only speed.
  * "blocked_tile": 0 auto, 64 = 128x64-pixel regions, 34 = 128x32 regions with 2 rows per warp, 32 = 128x32 with 4 rows per warp;
  * "blocked_tma": 1 (default) TMA-fed persistent form of the 128x64 kernel, 0 = plain LDG form;
- * "resident_two_sweep": 1 = two sweeps per neighbour exchange in the cluster-resident kernel, 0 (default) = one;
  * "resident_warps": target warps per CTA of the cluster-resident kernel (default 8);
  * "pdl": 1 (default) sweep passes are chained with programmatic dependent launch, 0 = plain stream order;
  * "strip_residual": 1 = rtdd_strip_pass also fills the level's residual word (rtdd_level_residual), default 0;

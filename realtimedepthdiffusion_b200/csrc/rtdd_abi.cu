@@ -249,6 +249,7 @@ int enqueue_level(rtdd_ctx *ctx, cudaStream_t s, const LevelArgs &a, bool captur
         if (rc) return rc;
         RTDD_TRY(cudaEventRecordWithFlags(L.evEnd, s, flags), "level event");
         L.timed = true; L.lastIters = a.iters; L.lastKernels = k;
+        ctx->captureTiming.push_back({a.level, a.iters, k});
         n += k;
     }
     if (!direct) {
@@ -276,6 +277,7 @@ int run_cached_graph(rtdd_ctx *ctx, const RtddGraphKey &key, Body body)
         cudaStream_t cs = ctx->captureStream;
         RTDD_TRY(cudaStreamBeginCapture(cs, cudaStreamCaptureModeRelaxed), "cudaStreamBeginCapture");
         int kernels = 0;
+        ctx->captureTiming.clear();
         const int rc = body(cs, &kernels);
         cudaGraph_t graph = nullptr;
         const cudaError_t e2 = cudaStreamEndCapture(cs, &graph);
@@ -286,9 +288,15 @@ int run_cached_graph(rtdd_ctx *ctx, const RtddGraphKey &key, Body body)
         cudaGraphDestroy(graph);
         RTDD_TRY(e, "cudaGraphInstantiate");
         g.kernels = kernels;
+        g.timing = ctx->captureTiming;
         it = ctx->graphs.emplace(key, g).first;
     }
     RTDD_TRY(cudaGraphLaunch(it->second.exec, ctx->stream), "cudaGraphLaunch");
+    // the level events now bracket THIS graph's sweeps: rtdd_level_sweep_ms must pair them with this graph's counts
+    for (const RtddLevelTiming &t : it->second.timing) {
+        RtddLevel &L = ctx->lv[t.level];
+        L.timed = true; L.lastIters = t.iters; L.lastKernels = t.kernels;
+    }
     ctx->launches += it->second.kernels;
     return 0;
 }
@@ -358,7 +366,7 @@ int rtdd_plan_strips(const int *levelRows, const int *levelCols, int levels, int
 // RTDD_E_* when `capacity` is too small).
 int rtdd_strip_schedule(int iters, int halo, int passSweeps, int level, int *sweepsOfPass, int *exchangeAfter, int capacity)
 {
-    if (iters < 0 || halo < 1 || level < 0 || !sweepsOfPass || !exchangeAfter) return -RTDD_E_ARG;
+    if (iters < 0 || halo < 1 || level < 0 || !sweepsOfPass || !exchangeAfter || capacity < 0) return RTDD_E_ARG;
     int T = passSweeps;
     if (T < 1 || T > halo) T = halo;
     int k = 0, since = 0, n = 0;
@@ -366,7 +374,7 @@ int rtdd_strip_schedule(int iters, int halo, int passSweeps, int level, int *swe
         int m = T;
         if (iters - k < m) m = iters - k;
         if (halo - since < m) m = halo - since;
-        if (n >= capacity) return -RTDD_E_ARG;
+        if (n >= capacity) return RTDD_E_ARG;
         k += m;
         since += m;
         const bool exchange = (since >= halo || k >= iters) && (k < iters || level > 0);
@@ -423,6 +431,7 @@ int rtdd_create(int rows, int cols, int levels, int device, rtdd_ctx **out)
     ctx->dLut = (float *)p;
     p += rtdd_round_up(257 * sizeof(float), 256);
     unsigned int *resWords = (unsigned int *)p;
+    ctx->dErrWord = resWords + 63;                     // <= 30 levels use words 0..29
     p += 256;
     unsigned int *stripWords = (unsigned int *)p;      // 16 words per level (same offset in every rank's arena)
     p += 2048;
@@ -437,6 +446,7 @@ int rtdd_create(int rows, int cols, int levels, int device, rtdd_ctx **out)
         L.stage = (float *)p;   p += rtdd_round_up((size_t)8 * RTDD_MAX_HALO * L.pitchF * sizeof(float), 256);
     }
     build_tensor_maps(ctx);
+    e = rtdd::configure_kernels();
     for (int l = 0; l < levels && e == cudaSuccess; l++) {
         e = cudaEventCreate(&ctx->lv[l].evBegin);
         if (e == cudaSuccess) e = cudaEventCreate(&ctx->lv[l].evEnd);
@@ -457,6 +467,7 @@ int rtdd_destroy(rtdd_ctx *ctx)
         if (L.evBegin) cudaEventDestroy(L.evBegin);
         if (L.evEnd) cudaEventDestroy(L.evEnd);
     }
+    for (void *p : ctx->ipcImports) cudaIpcCloseMemHandle(p);
     if (ctx->dOmega) cudaFree(ctx->dOmega);
     if (ctx->arena) cudaFree(ctx->arena);
     if (ctx->frameArena) cudaFree(ctx->frameArena);
@@ -493,6 +504,15 @@ int rtdd_sync(rtdd_ctx *ctx)
     DeviceGuard guard(ctx->device);
     RTDD_TRY(cudaStreamSynchronize(ctx->stream), "rtdd_sync");
     RTDD_TRY(cudaGetLastError(), "rtdd_sync");
+    if (ctx->peerUp || ctx->peerDn) {
+        // strip mode: a halo wait that gave up (spin_timeout_ms) left a mark instead of killing the context
+        unsigned int w = 0;
+        RTDD_TRY(cudaMemcpy(&w, ctx->dErrWord, sizeof(w), cudaMemcpyDeviceToHost), "rtdd_sync");
+        if (w == RTDD_SPIN_TIMED_OUT) {
+            cudaMemset(ctx->dErrWord, 0, sizeof(w));
+            return rtdd_fail(ctx, RTDD_E_PEER, "rtdd_sync (a halo wait on a neighbouring rank timed out; ghost rows are stale)");
+        }
+    }
     return 0;
 }
 
@@ -535,15 +555,12 @@ int rtdd_set_tuning(rtdd_ctx *ctx, const char *key, int value)
         ctx->stripResidual = (value != 0);
         return 0;
     }
-    if (strcmp(key, "strip_peer_staging") == 0 && (value == 0 || value == 1)) {
-        ctx->peerStaging = (value != 0);
+    if (strcmp(key, "spin_timeout_ms") == 0 && value >= 0) {
+        ctx->spinTimeoutMs = (unsigned int)value;
         return 0;
     }
-    if (strcmp(key, "resident_two_sweep") == 0 && (value == 0 || value == 1)) {
-        rtdd::set_resident_two_sweep(value);
-        DeviceGuard guard(ctx->device);
-        cudaStreamSynchronize(ctx->stream);
-        destroy_graphs(ctx);
+    if (strcmp(key, "strip_peer_staging") == 0 && (value == 0 || value == 1)) {
+        ctx->peerStaging = (value != 0);
         return 0;
     }
     if (strcmp(key, "pdl") == 0 && (value == 0 || value == 1)) {
@@ -755,7 +772,9 @@ int rtdd_ipc_import(rtdd_ctx *ctx, const void *handle64, void **peerArena)
     cudaIpcMemHandle_t h;
     memcpy(&h, handle64, sizeof(h));
     const int rc = rtdd_check(ctx, cudaIpcOpenMemHandle(peerArena, h, cudaIpcMemLazyEnablePeerAccess), "rtdd_ipc_import");
-    return rc ? rtdd_fail(ctx, RTDD_E_PEER, "rtdd_ipc_import (cudaIpcOpenMemHandle)") : 0;
+    if (rc) return rtdd_fail(ctx, RTDD_E_PEER, "rtdd_ipc_import (cudaIpcOpenMemHandle)");
+    ctx->ipcImports.push_back(*peerArena);
+    return 0;
 }
 
 int rtdd_arena(rtdd_ctx *ctx, void **base, size_t *bytes)
@@ -857,7 +876,7 @@ int rtdd_strip_pull(rtdd_ctx *ctx, int level)
         dn.rows = H;
         waitDn = L.dStripWords + 6;
     }
-    RTDD_TRY(rtdd::launch_halo_pull(ctx->stream, up, dn, L.pitchF, waitUp, waitDn, L.peerSeq + 1u), "rtdd_strip_pull");
+    RTDD_TRY(rtdd::launch_halo_pull(ctx->stream, up, dn, L.pitchF, waitUp, waitDn, L.peerSeq + 1u, ctx->dErrWord, ctx->spinTimeoutMs), "rtdd_strip_pull");
     L.peerSeq++;
     ctx->launches++;
     return 0;
@@ -880,7 +899,7 @@ int rtdd_strip_wait(rtdd_ctx *ctx, int level)
     DeviceGuard guard(ctx->device);
     const unsigned int *wu = (ctx->peerUp && L.stripUpWinBegin >= 0) ? L.dStripWords + 1 : nullptr;
     const unsigned int *wd = (ctx->peerDn && L.stripDnWinBegin >= 0) ? L.dStripWords + 2 : nullptr;
-    RTDD_TRY(rtdd::launch_halo_wait(ctx->stream, wu, wd, L.stripPassAbs), "rtdd_strip_wait");
+    RTDD_TRY(rtdd::launch_halo_wait(ctx->stream, wu, wd, L.stripPassAbs, ctx->dErrWord, ctx->spinTimeoutMs), "rtdd_strip_wait");
     ctx->launches++;
     return 0;
 }
@@ -926,20 +945,29 @@ int rtdd_strip_pass(rtdd_ctx *ctx, int level, int firstSweep, int nsweeps, int h
         hp.storeHi = 0x7FFFFFFF;
         if (ctx->peerUp && L.stripUpWinBegin >= 0) hp.storeLo = gt;       // the rank above fills my upper ghost rows
         if (ctx->peerDn && L.stripDnWinBegin >= 0) hp.storeHi = own1;     // the rank below fills my lower ghost rows
-        if (ctx->peerUp && L.stripUpWinBegin >= 0 && !L.stripPushOff) {
-            hp.upX = (float *)(ctx->peerUp + offX); hp.upP = (float *)(ctx->peerUp + offP);
-            hp.upLo = gt; hp.upHi = gt + H;
-            hp.upDelta = L.stripBegin - L.stripUpWinBegin;                   // window-local row -> neighbour's window-local row
+        // The waits and the completion flags belong to the NEIGHBOUR RELATION, not to the push: a pass that keeps its
+        // boundary rows to itself (stripPushOff, the finest level's last pass) still reads ghost rows its neighbours pushed
+        // during the previous pass, so it must wait for them, and it still raises its flags (rtdd.h).
+        if (ctx->peerUp && L.stripUpWinBegin >= 0) {
+            if (!L.stripPushOff) {
+                hp.upX = (float *)(ctx->peerUp + offX); hp.upP = (float *)(ctx->peerUp + offP);
+                hp.upLo = gt; hp.upHi = gt + H;
+                hp.upDelta = L.stripBegin - L.stripUpWinBegin;               // window-local row -> neighbour's window-local row
+            }
             hp.upFlag = (unsigned int *)(ctx->peerUp + offW) + 2;            // "written by the rank below"
             hp.waitUp = L.dStripWords + 1;
         }
-        if (ctx->peerDn && L.stripDnWinBegin >= 0 && !L.stripPushOff) {
-            hp.dnX = (float *)(ctx->peerDn + offX); hp.dnP = (float *)(ctx->peerDn + offP);
-            hp.dnLo = own1 - H; hp.dnHi = own1;
-            hp.dnDelta = L.stripBegin - L.stripDnWinBegin;
+        if (ctx->peerDn && L.stripDnWinBegin >= 0) {
+            if (!L.stripPushOff) {
+                hp.dnX = (float *)(ctx->peerDn + offX); hp.dnP = (float *)(ctx->peerDn + offP);
+                hp.dnLo = own1 - H; hp.dnHi = own1;
+                hp.dnDelta = L.stripBegin - L.stripDnWinBegin;
+            }
             hp.dnFlag = (unsigned int *)(ctx->peerDn + offW) + 1;            // "written by the rank above"
             hp.waitDn = L.dStripWords + 2;
         }
+        hp.err = ctx->dErrWord;
+        hp.timeoutMs = ctx->spinTimeoutMs;
         hp.counter = L.dStripWords;
         hp.doneTarget = L.stripCtaAbs;                                       // the launcher adds this pass's CTA count
         hp.flagValue = L.stripPassAbs + 1;

@@ -67,10 +67,12 @@ struct RtddGraphKey {
     }
 };
 
+struct RtddLevelTiming { int level, iters, kernels; };
 struct RtddGraph {
     cudaGraphExec_t exec = nullptr;
     int kernels = 0;
     int resultPlane = 0;   // index into RtddLevel::x holding x_K after the graph ran
+    std::vector<RtddLevelTiming> timing;   // what rtdd_level_sweep_ms reports after THIS graph ran (copied into the levels at every launch)
 };
 
 struct rtdd_ctx {
@@ -88,10 +90,14 @@ struct rtdd_ctx {
     bool lutLoaded = false;
     int variant = 0;             // 0 auto, 1 single-sweep, 2 temporally blocked, 3 cluster-resident
     char *peerUp = nullptr, *peerDn = nullptr;   // neighbours' arenas (IPC-mapped or same-process), same layout as `arena`
+    std::vector<void *> ipcImports;              // arenas mapped by rtdd_ipc_import (closed in rtdd_destroy)
+    unsigned int *dErrWord = nullptr;            // device word: RTDD_SPIN_TIMED_OUT once a halo wait gave up
+    unsigned int spinTimeoutMs = 20000;          // rtdd_set_tuning("spin_timeout_ms", ...)
     float *dOmega = nullptr;     // the omega schedule (prefix-stable), dOmegaCap entries
     int dOmegaCap = 0;
     int sweepsPerPass = 0;       // 0 auto
     std::map<RtddGraphKey, RtddGraph> graphs;
+    std::vector<RtddLevelTiming> captureTiming;   // filled by enqueue_level while a graph is being captured
     unsigned long long launches = 0;
     std::string err;
     // frame driver state
@@ -138,7 +144,10 @@ struct HaloPush {
     unsigned int flagValue;
     const unsigned int *waitUp, *waitDn;   // this rank's flags: spin until >= waitValue before touching ghost rows (0 = no wait)
     unsigned int waitValue;
+    unsigned int *err;                     // context error word: a wait that timed out stores RTDD_SPIN_TIMED_OUT here
+    unsigned int timeoutMs;                // 0 = wait for ever
 };
+#define RTDD_SPIN_TIMED_OUT 0x51A1u
 cudaError_t launch_level_prolong_init(cudaStream_t s, const RtddLevel &L, const float *src, size_t srcPitch, int srows, int scols,
                                       const uint8_t *edited, size_t editedPitch, const uint8_t *scribble, size_t scribblePitch,
                                       const uint8_t *gray, size_t grayPitch, int threshold, float *x0, unsigned int *residual);
@@ -163,8 +172,13 @@ struct HaloRows {
 cudaError_t launch_halo_push(cudaStream_t s, HaloRows up, HaloRows dn, int pitchF, unsigned int *ticket,
                              unsigned int *upFlag, unsigned int *dnFlag, unsigned int flagValue);
 cudaError_t launch_halo_pull(cudaStream_t s, HaloRows up, HaloRows dn, int pitchF, const unsigned int *waitUp, const unsigned int *waitDn,
-                             unsigned int value);
-cudaError_t launch_halo_wait(cudaStream_t s, const unsigned int *waitUp, const unsigned int *waitDn, unsigned int value);
+                             unsigned int value, unsigned int *err, unsigned int timeoutMs);
+cudaError_t launch_halo_wait(cudaStream_t s, const unsigned int *waitUp, const unsigned int *waitDn, unsigned int value,
+                             unsigned int *err, unsigned int timeoutMs);
+// per-device function attributes (cluster size, dynamic shared memory) of every kernel that needs them; called once per
+// context from rtdd_create with the context's device current (no lazily initialised statics: contexts may be created
+// from several host threads, one per GPU)
+cudaError_t configure_kernels();
 int blocked_max_T();
 void set_blocked_tile_override(int tile);
 void set_blocked_tma(int enabled);
@@ -191,7 +205,6 @@ static inline cudaError_t launch_pdl(Kernel kernel, dim3 grid, dim3 block, size_
     cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kernel, args...);
 }
-void set_resident_two_sweep(int on);
 // resident (one cluster, all sweeps in one launch); omegas = device array of nsweeps floats
 bool resident_plan(int rows, int cols, int *R, int *clusterSize, int *blocksPerCta, int *WX);
 cudaError_t launch_sweep_resident(cudaStream_t s, const RtddLevel &L, const float *lut, const float *x, float *xOut,

@@ -97,6 +97,20 @@ def test_native_planning_matches_its_restatement():
     assert [e for _, e in strips.strip_schedule(31, 8, 0, 3)] == [True, True, True, True]
 
 
+def test_strip_schedule_errors_are_negative():
+    """rtdd.h: errors are negative (RTDD_E_ARG = -1), never confusable with a pass count."""
+    import ctypes as C
+    from realtimedepthdiffusion_b200._native import lib
+    buf = (C.c_int * 4)()
+    assert lib.rtdd_strip_schedule(-1, 8, 8, 0, buf, buf, 4) == -1            # negative sweep count
+    assert lib.rtdd_strip_schedule(10, 0, 8, 0, buf, buf, 4) == -1            # halo < 1
+    assert lib.rtdd_strip_schedule(10, 8, 8, -1, buf, buf, 4) == -1           # negative level
+    assert lib.rtdd_strip_schedule(10, 8, 8, 0, None, buf, 4) == -1           # null output
+    assert lib.rtdd_strip_schedule(64, 8, 8, 0, buf, buf, 4) == -1            # 8 passes do not fit a capacity of 4
+    assert lib.rtdd_strip_schedule(32, 8, 8, 0, buf, buf, 4) == 4             # exactly fits
+    assert lib.rtdd_strip_schedule(0, 8, 8, 0, buf, buf, 0) == 0              # no sweeps: no passes
+
+
 @pytest.mark.parametrize("rows,cols,nranks,halo,iters", [(203, 150, 2, 4, 70), (256, 96, 3, 8, 100), (181, 130, 2, 5, 33)])
 def test_lockstep_strips_are_bit_identical_to_the_single_solve(rows, cols, nranks, halo, iters):
     bgr, scribble, edited = synth.synth_case(rows, cols, 321)

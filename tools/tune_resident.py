@@ -17,9 +17,8 @@ for rows, cols, iters in ((67, 120, 1000), (135, 240, 500), (64, 64, 1000), (128
     scribble = np.where(rng.random((rows, cols)) < 0.1, 255, 0).astype(np.uint8)
     d0, s, g = to_dev(depth), to_dev(scribble), to_dev(gray)
     line = []
-    for two, w in ((0, 8), (1, 4), (1, 6), (1, 8), (1, 12), (1, 16)):
+    for w in (4, 6, 8, 12, 16):
         ctx = rtdd.DepthDiffusion(rows, cols, 1)
-        ctx.set_tuning("resident_two_sweep", two)
         ctx.set_tuning("resident_warps", w)
         ctx.set_sweep_variant(3, 0)
         d = d0.clone()
@@ -29,8 +28,7 @@ for rows, cols, iters in ((67, 120, 1000), (135, 240, 500), (64, 64, 1000), (128
                 ctx.matrix_free_solver(d, s, g, iters, 0)
             ctx.sync()
             ms.append(ctx.level_sweep_ms(0)[0])
-        line.append("two%d w%d %.4f" % (two, w, float(np.median(ms))))
+        line.append("w%d %.4f" % (w, float(np.median(ms))))
         ctx.set_tuning("resident_warps", 8)
-        ctx.set_tuning("resident_two_sweep", 0)
         ctx.close()
     print("%dx%d x%d: " % (cols, rows, iters) + "  ".join(line), flush=True)
