@@ -120,20 +120,34 @@ def max_over_ranks(dist, v):
     return float(t.item())
 
 
+def pyramid_levels(rows, cols):
+    """ref: src/main.cpp:95"""
+    import math
+    return int(math.log2(max(min(cols, rows) // 45, 1))) + 1
+
+
 def pixel_sweeps(rows, cols, levels, max_iterations=1000):
-    from realtimedepthdiffusion_b200 import level_iterations, level_sizes
+    """Level sizes (ref: src/main.cpp:103 floor), sweeps per level (ref: src/main.cpp:263) and their product -- plain
+    arithmetic, shared by both arms (the reference arm must not import the product package)."""
     total, per = 0, []
-    for l, (r, c) in enumerate(level_sizes(rows, cols, levels)):
-        it = level_iterations(max_iterations, levels, l)
+    for l in range(levels):
+        r, c = int(rows / 2.0 ** l), int(cols / 2.0 ** l)
+        it = int(np.float32(max_iterations) / np.float32(2.0 ** ((levels - 1) - l)))
         per.append((r, c, it))
         total += r * c * it
     return total, per
 
 
+def workload_string(rows, cols, seed, levels, per_level, total_ps):
+    return ("configs[2]: %dx%d synthetic image (seed %d+rank) + ~10%% brush scribbles, full %d-level pyramid solve, "
+            "reference schedule %s sweeps = %.1f M pixel-sweeps per solve; N>1 = configs[3] batch data parallelism "
+            "(one image per rank, no collective)" % (cols, rows, seed, levels, "/".join(str(p[2]) for p in reversed(per_level)), total_ps / 1e6))
+
+
 def cpu_baseline(rows, cols, levels, budget_s=12.0):
     """The oracle port (OpenMP) on the host cores: level-0 sweeps of the same workload, bounded."""
     from oracle import binding as ob
-    from realtimedepthdiffusion_b200 import level_iterations, synth
+    synth = ob.pkg_file("synth")
     bgr, scribble, edited = synth.synth_case(rows, cols, 1003)
     gray = ob.bgr2gray(bgr)
     depth = np.full((rows, cols), 255.0, np.float32)
@@ -143,7 +157,7 @@ def cpu_baseline(rows, cols, levels, budget_s=12.0):
         ob.set_num_threads(len(os.sched_getaffinity(0)))       # torchrun exports OMP_NUM_THREADS=1: use every core we may run on
     except AttributeError:
         ob.set_num_threads(os.cpu_count() or 1)
-    iters = level_iterations(1000, levels, 0)
+    iters = pixel_sweeps(rows, cols, levels)[1][0][2]
     ob.solve_level(depth[:64], scribble[:64], gray[:64], 2, 0, levels - 1, lut)     # warm the OpenMP pool
     t0 = time.perf_counter()
     done = 0
@@ -158,17 +172,79 @@ def cpu_baseline(rows, cols, levels, budget_s=12.0):
             "sample": "%dx%d level 0, %d Chebyshev-Jacobi sweeps incl. edge-weight pass, OpenMP static rows, %.1f s" % (cols, rows, done, el)}
 
 
+def batch256_1080p(rtdd, dist, rank, world, stream_main):
+    """BASELINE configs[3] as written: 256 synthetic 1080p images, seeds 2000..2255, ~10 % scribbles,
+    image i -> rank i mod N; every image is a full job through the public API from pinned HOST buffers -- BGR upload + gray
+    pyramid (rtdd_frame_set_image), annotation upload + ingest + 5-level solve (rtdd_frame_solve_host_annotation) and the
+    8-bit map back (rtdd_frame_read_depth_u8) -- with K independent contexts in flight per GPU (one stream each, one host
+    thread).  Images are synthesised on the device beforehand (outside the timed region) and parked in pinned memory."""
+    from realtimedepthdiffusion_b200 import synth_device
+    rows, cols, total_images, K = 1080, 1920, 256, 6
+    mine = list(range(rank, total_images, world))
+    gen = rtdd.DepthDiffusion(rows, cols)
+    gen.set_stream(stream_main)
+    h_bgr, h_ann = [], []
+    with torch.cuda.stream(stream_main):
+        for i in mine:
+            bgr, scribble, edited = synth_device.synth_case_device(rows, cols, 2000 + i, gen)
+            hb = torch.empty((rows, cols, 3), dtype=torch.uint8).pin_memory()
+            hb.view(rows, cols * 3).copy_(bgr)
+            ha = torch.empty((rows, cols), dtype=torch.uint8).pin_memory()
+            ha.copy_(synth_device.annotation_plane_device(scribble, edited))
+            h_bgr.append(hb)
+            h_ann.append(ha)
+        torch.cuda.synchronize()
+    levels = gen.levels
+    gen.close()
+    per_image_ps, _ = pixel_sweeps(rows, cols, levels)
+    ctxs = []
+    for k in range(K):
+        c = rtdd.DepthDiffusion(rows, cols)
+        st = torch.cuda.Stream()
+        c.set_stream(st)
+        ctxs.append((c, st, torch.empty((rows, cols), dtype=torch.uint8).pin_memory()))
+    for k, (c, st, ho) in enumerate(ctxs):                       # warm-up: graphs, allocations
+        c.frame_set_image(h_bgr[k % len(mine)])
+        c.frame_solve_host_annotation(h_ann[k % len(mine)], 1000, ho)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier(dist)
+    ev0.record()
+    for _, st, _ in ctxs:
+        st.wait_event(ev0)
+    launches0 = sum(c.launch_count for c, _, _ in ctxs)
+    for j in range(len(mine)):
+        c, st, ho = ctxs[j % K]
+        c.frame_set_image(h_bgr[j], sync=False)
+        c.frame_solve_host_annotation(h_ann[j], 1000, None)
+        c.frame_read_depth_u8(ho, sync=False)
+    for _, st, _ in ctxs:
+        torch.cuda.current_stream().wait_stream(st)
+    ev1.record()
+    torch.cuda.synchronize()
+    launches = sum(c.launch_count for c, _, _ in ctxs) - launches0
+    ms = max_over_ranks(dist, ev0.elapsed_time(ev1))
+    for c, _, _ in ctxs:
+        c.close()
+    return {"images": total_images, "images_per_gpu": len(mine), "contexts_in_flight_per_gpu": K, "ms_total": ms, "ms_per_image": ms / total_images,
+            "value": per_image_ps * total_images / (ms * 1e-3) / 1e6, "unit": "Mpixel-sweeps/s", "gpu_launches_rank0": int(launches),
+            "h2d_bytes_per_image": rows * cols * 4, "d2h_bytes_per_image": rows * cols,
+            "note": "256 x (1920x1080, %d levels, %.1f M pixel-sweeps) from pinned host buffers through rtdd_frame_set_image + "
+                    "rtdd_frame_solve_host_annotation + rtdd_frame_read_depth_u8; uploads, gray pyramid and downloads inside the timed region"
+                    % (levels, per_image_ps / 1e6)}
+
+
 def run_native(args, dist, rank, world, local):
     import realtimedepthdiffusion_b200 as rtdd
     from realtimedepthdiffusion_b200 import synth
     rows, cols, seed = WORKLOADS[args.workload]
-    # configs[3]: image i -> rank i mod N; every rank gets its own seed
+    # N > 1: image i -> rank i mod N; every rank gets its own seed
     bgr, scribble, edited = synth.synth_case(rows, cols, seed + rank + args.seed_offset)
     ctx = rtdd.DepthDiffusion(rows, cols)
     stream = torch.cuda.Stream()
     ctx.set_stream(stream)
     total_ps, per_level = pixel_sweeps(rows, cols, ctx.levels)
     ctx.frame_set_image(bgr)
+    h_ann = torch.from_numpy(synth.annotation_plane(scribble, edited)).pin_memory()
     h_scr = torch.from_numpy(scribble).pin_memory()
     h_edt = torch.from_numpy(edited).pin_memory()
     h_out = torch.zeros((rows, cols), dtype=torch.uint8).pin_memory()
@@ -176,7 +252,7 @@ def run_native(args, dist, rank, world, local):
 
     with torch.cuda.stream(stream):
         # ---- device-resident arm ---------------------------------------------------------------
-        ctx.frame_solve_host(h_scr, h_edt, 1000, h_out)          # uploads the annotations once, builds graphs
+        ctx.frame_solve_host_annotation(h_ann, 1000, h_out)      # uploads the annotation once, builds graphs
         for _ in range(args.warmup):
             ctx.frame_solve(1000)
         ctx.sync()
@@ -194,22 +270,26 @@ def run_native(args, dist, rank, world, local):
         ms_dev = max_over_ranks(dist, ev0.elapsed_time(ev1) / args.steps)
         lvl_ms = [ctx.level_sweep_ms(l) for l in range(ctx.levels)]
 
-        # ---- end-to-end arm (host buffers, copies inside the timed region) -------------------------
-        for _ in range(max(args.warmup // 2, 1)):
-            ctx.frame_solve_host(h_scr, h_edt, 1000, h_out)
-        barrier(dist)
-        l0_ms = []
-        t_e2e = []
-        for _ in range(args.steps):
-            ev0.record(stream)
-            ctx.frame_solve_host(h_scr, h_edt, 1000, h_out)       # synchronous: returns after the download
-            ev1.record(stream)
-            ev1.synchronize()
-            t_e2e.append(ev0.elapsed_time(ev1))
-            l0_ms.append(ctx.level_sweep_ms(0)[0])
-        barrier(dist)
+        # ---- end-to-end arm: the public call with HOST buffers, copies inside the timed region -----------------------
+        def time_e2e(call):
+            for _ in range(max(args.warmup // 2, 1)):
+                call()
+            barrier(dist)
+            t, l0 = [], []
+            for _ in range(args.steps):
+                ev0.record(stream)
+                call()                                            # synchronous: returns after the download
+                ev1.record(stream)
+                ev1.synchronize()
+                t.append(ev0.elapsed_time(ev1))
+                l0.append(ctx.level_sweep_ms(0)[0])
+            barrier(dist)
+            return max_over_ranks(dist, float(np.mean(t))), l0
+        # the reference's persistent annotation format: ONE plane, 32 = not annotated (main.cpp:160-170), expanded on the device
+        ms_e2e, l0_ms = time_e2e(lambda: ctx.frame_solve_host_annotation(h_ann, 1000, h_out))
+        # main.cpp's own per-frame traffic (scribble + 3-channel edited, main.cpp:236-237), kept for drop-in parity
+        ms_e2e3, _ = time_e2e(lambda: ctx.frame_solve_host(h_scr, h_edt, 1000, h_out))
         clocks = sampler.stop()
-        ms_e2e = max_over_ranks(dist, float(np.mean(t_e2e)))
 
         # ---- effects on the solved depth (configs[2]'s second half), reported beside the solve ----
         eff = {}
@@ -252,38 +332,8 @@ def run_native(args, dist, rank, world, local):
             ms = t_eff(lambda: (ctx.frame_solve(1000), L.rtdd_frame_effects(ctx._h, o[0][0], o[0][1], o[1][0], o[1][1], o[2][0], o[2][1])), reps=10)
             eff["solve_plus_effects_frame"] = {"ms": ms}
 
-    # ---- configs[3] on one GPU: several independent images in flight (one context + stream each).  The coarse levels
-    #      occupy <= 16 SMs for most of their 1500 sweeps, so other images' levels fill the rest of the GPU.
-    K = 4
-    extra = []
-    for k in range(1, K):
-        b2, s2, e2 = synth.synth_case(rows, cols, seed + 100 * (k + 1) + rank)
-        c2 = rtdd.DepthDiffusion(rows, cols)
-        st2 = torch.cuda.Stream()
-        c2.set_stream(st2)
-        c2.frame_set_image(b2)
-        c2.frame_solve_host(s2, e2, 1000, None)
-        extra.append((c2, st2))
-    group = [(ctx, stream)] + extra
-    for c, _ in group:
-        c.frame_solve(1000)
-    barrier(dist)
-    nframes = 6 * K
-    ev0.record()
-    for _, st in group:
-        st.wait_event(ev0)
-    for f in range(nframes):
-        group[f % K][0].frame_solve(1000)
-    for _, st in group:
-        torch.cuda.current_stream().wait_stream(st)
-    ev1.record()
-    torch.cuda.synchronize()
-    ms_batch = max_over_ranks(dist, ev0.elapsed_time(ev1))
-    batch = {"contexts_per_gpu": K, "frames_per_gpu": nframes, "ms_per_frame": ms_batch / nframes,
-             "value": total_ps * nframes * world / (ms_batch * 1e-3) / 1e6, "unit": "Mpixel-sweeps/s",
-             "note": "configs[3]-style throughput: %d independent images in flight per GPU (one context and stream each), device-resident" % K}
-    for c, _ in extra:
-        c.close()
+    batch = None if args.no_batch else batch256_1080p(rtdd, dist, rank, world, stream)
+    strips = None if args.no_strips else strips16k_record(rtdd, dist, rank, world, stream, args)
 
     peak, peak_src = peaks()
     r0, c0, it0 = per_level[0]
@@ -294,40 +344,51 @@ def run_native(args, dist, rank, world, local):
         "metric": "Mpixel-sweeps/s", "value": total_ps * world / (ms_dev * 1e-3) / 1e6, "unit": "Mpixel-sweeps/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev, "ms_per_solve": ms_dev,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "configs[2]: %dx%d synthetic image (seed %d+rank) + ~10%% brush scribbles, full %d-level pyramid solve, "
-                               "reference schedule %s sweeps = %.1f M pixel-sweeps per solve; N>1 = configs[3] batch data parallelism "
-                               "(one image per rank, no collective)" % (cols, rows, seed, ctx.levels,
-                                                                        "/".join(str(p[2]) for p in reversed(per_level)), total_ps / 1e6),
+        "config": {"workload": workload_string(rows, cols, seed, ctx.levels, per_level, total_ps),
                    "l2": "no explicit flush: the solve streams a %.0f MB working set (> 126 MB L2) and every level's planes are rewritten each step"
                          % (sum(r * c for r, c, _ in per_level) * 19 / 1e6),
                    "parallelism": "dp%d" % world},
         "e2e": {"value": total_ps * world / (ms_e2e * 1e-3) / 1e6, "unit": "Mpixel-sweeps/s", "ms_per_solve": ms_e2e,
-                "h2d_bytes_per_step": int(h_scr.numel() + h_edt.numel()), "d2h_bytes_per_step": int(h_out.numel())},
+                "h2d_bytes_per_step": int(h_ann.numel()), "d2h_bytes_per_step": int(h_out.numel()),
+                "call": "rtdd_frame_solve_host_annotation: the annotation as ONE u8 plane (32 = not annotated, main.cpp:160-170) from pinned host "
+                        "memory, expanded on the device; 8-bit depth map back to pinned host memory",
+                "three_plane_upload": {"ms_per_solve": ms_e2e3, "value": total_ps * world / (ms_e2e3 * 1e-3) / 1e6,
+                                       "h2d_bytes_per_step": int(h_scr.numel() + h_edt.numel()),
+                                       "call": "rtdd_frame_solve_host: scribble + 3-channel edited planes, main.cpp:236-237's own traffic"}},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": "sweep_blocked_tma_kernel (level 0, %dx%d, %d sweeps in %d launches)" % (c0, r0, it0, k0),
+        "roofline": {"bound": "hbm", "limiter": "instruction issue (see note)",
+                     "kernel": "level-0 sweep kernel (%dx%d, %d sweeps in %d launches)" % (c0, r0, it0, k0),
                      "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH.get(args.workload), "algorithmic_bytes_per_launch": BYTES_PER_PIXEL_SWEEP * r0 * c0 * it0 / k0,
                      "avg_launch_ms": l0 / k0,
                      "note": "achieved = 17 B x pixel-sweeps / time is the EFFECTIVE sweep bandwidth (SURVEY.md 8d): the kernel is temporally "
-                             "blocked (8 sweeps per HBM round trip), so its real DRAM traffic (`traffic`, ncu) is ~8.5x below the algorithmic "
-                             "bytes and frac may exceed 1; the kernel is issue-bound, not HBM-bound (profiles/r01_ncu_*.txt)"},
+                             "blocked (several sweeps per HBM round trip), so its real DRAM traffic (`traffic`, ncu, per launch; null when no "
+                             "capture exists for this workload) is far below the algorithmic bytes and frac may exceed 1; the kernel is "
+                             "issue-bound, not HBM-bound (profiles/)"},
         "levels": [{"level": l, "size": "%dx%d" % (per_level[l][1], per_level[l][0]), "sweeps": per_level[l][2], "ms": lvl_ms[l][0],
                     "launches": lvl_ms[l][2], "us_per_sweep": 1e3 * lvl_ms[l][0] / max(per_level[l][2], 1),
                     "Gpixel-sweeps/s": per_level[l][0] * per_level[l][1] * per_level[l][2] / (lvl_ms[l][0] * 1e-3) / 1e9}
                    for l in range(ctx.levels)],
         "effects": eff,
-        "batch_concurrent": batch,
+        "batch256_1080p": batch,
+        "strips16k": strips,
         "clocks": clocks,
     }
     ctx.close()
     return line
 
 
+def strips16k_record(rtdd, dist, rank, world, stream, args):
+    """BASELINE configs[4]: filled in by the row-strip driver (see below)."""
+    return None
+
+
 def run_reference(args, dist, rank, world, local):
-    """The reference's own kernels through the reference's own functions (libref.so)."""
+    """The reference's own kernels through the reference's own functions (libref.so).  Nothing of the product is imported
+    here: synth / planes / refnames are loaded by path (oracle.binding.pkg_file), so librtdd.so is not in this process."""
     from oracle import binding as ob
     from oracle.mainloop import MainLoop, pitch, ptr
-    from realtimedepthdiffusion_b200 import synth
+    synth = ob.pkg_file("synth")
     if rank != 0:
         return None
     if not os.path.exists(ob.LIBREF):
@@ -371,8 +432,7 @@ def run_reference(args, dist, rank, world, local):
             h_out.copy_(q, non_blocking=True)
             torch.cuda.synchronize()
 
-    steps = max(min(args.steps, 10), 1)
-    warm = max(min(args.warmup, 3), 1)
+    steps, warm = args.steps, args.warmup
     for _ in range(warm):
         gpu_frame(False)
     torch.cuda.synchronize()
@@ -384,7 +444,8 @@ def run_reference(args, dist, rank, world, local):
     ev1.record()
     torch.cuda.synchronize()
     ms_dev = ev0.elapsed_time(ev1) / steps
-    gpu_frame(True)
+    for _ in range(max(warm // 2, 1)):
+        gpu_frame(True)
     t = []
     for _ in range(steps):
         ev0.record()
@@ -416,13 +477,16 @@ def run_reference(args, dist, rank, world, local):
         "impl": "reference", "metric": "Mpixel-sweeps/s", "value": value, "unit": "Mpixel-sweeps/s", "n_gpus": 1, "steps": steps, "warmup": warm,
         "ms_per_step": ms_dev, "ms_per_solve": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": "configs[2]: %dx%d synthetic image (seed %d) + ~10%% brush scribbles, full %d-level pyramid solve through the "
-                               "reference's own GPU* functions (oracle/_ref/libref.so = /root/reference/src/*.cu unmodified, nvcc -O3 sm_100a); "
-                               "OpenCV pyrUp replaced by a device copy of the staged guess" % (cols, rows, seed, L),
-                   "parallelism": "dp1"},
+        "config": {"workload": workload_string(rows, cols, seed, L, per_level, total_ps),
+                   "l2": "no explicit flush: the solve streams a %.0f MB working set (> 126 MB L2) and every level's planes are rewritten each step"
+                         % (sum(r * c for r, c, _ in per_level) * 24 / 1e6),
+                   "parallelism": "dp1",
+                   "how": "the reference's own GPU* functions (oracle/_ref/libref.so = /root/reference/src/*.cu unmodified, nvcc -O3 sm_100a) driven by "
+                          "main.cpp's restated loop; OpenCV pyrUp replaced by a device copy of the staged guess (favours this arm); one GPU whatever "
+                          "--gpus says (the reference has no multi-GPU path)"},
         "e2e": {"value": total_ps / (ms_e2e * 1e-3) / 1e6, "unit": "Mpixel-sweeps/s", "ms_per_solve": ms_e2e,
                 "h2d_bytes_per_step": int(h_scr.numel() + h_edt.numel()), "d2h_bytes_per_step": int(h_out.numel()),
-                "note": "reference kernels run on the GPU; main.cpp's own per-frame uploads/downloads are inside the timed region"},
+                "note": "reference kernels run on the GPU; main.cpp's own per-frame uploads/downloads (:236-237, :291) are inside the timed region"},
         "gpu_launches": launches, "effects": eff, "clocks": clocks,
         "reference_device": "1x B200 (the reference has no CPU path; its own implementation is CUDA)",
     }
@@ -436,6 +500,8 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default="4k", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-batch", action="store_true", help="skip the configs[3] record (256 x 1080p)")
+    ap.add_argument("--no-strips", action="store_true", help="skip the configs[4] record (16384^2 row strips)")
     ap.add_argument("--seed-offset", type=int, default=0, help="extra offset on the synthetic image seed (diagnostics)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -466,7 +532,6 @@ def main():
     if rank == 0 and line is not None:
         if "unavailable" not in line and not args.no_cpu_baseline and (world == 1 or args.impl == "reference"):
             rows, cols, _ = WORKLOADS[args.workload]
-            from realtimedepthdiffusion_b200 import pyramid_levels
             line["cpu_baseline"] = cpu_baseline(rows, cols, pyramid_levels(rows, cols))
         emit(line)
     if dist is not None:

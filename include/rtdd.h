@@ -124,6 +124,10 @@ int rtdd_set_sweep_variant(rtdd_ctx *ctx, int variant, int sweepsPerPass);
 /* Process-wide tuning knobs for experiments (tools/tune_blocked.py); results never change, only speed.
  * "blocked_tile": 0 auto, 64 = 128x64-pixel regions, 34 = 128x32 regions with 2 rows per warp, 32 = 128x32 with 4 rows per warp;
  * "blocked_tma": 1 (default) TMA-fed persistent form of the 128x64 kernel, 0 = plain LDG form;
+ * "blocked_grid_cap": > 0 limits the persistent form to that many CTAs (tests: every CTA then walks several regions even on
+ *                     small levels, so the region loop -- phase flips, re-issue under the sweeps -- is checked against the oracle);
+ * "spin_timeout_ms": device-time limit of a halo wait on a neighbouring rank (default 20000, 0 = for ever); a wait that gives
+ *                    up marks the context and the next rtdd_sync returns RTDD_E_PEER instead of the context dying;
  * "resident_warps": target warps per CTA of the cluster-resident kernel (default 8);
  * "pdl": 1 (default) sweep passes are chained with programmatic dependent launch, 0 = plain stream order;
  * "strip_residual": 1 = rtdd_strip_pass also fills the level's residual word (rtdd_level_residual), default 0;
@@ -196,6 +200,13 @@ int rtdd_pyrdown_annotation(rtdd_ctx *ctx, const uint8_t *prevScribble, size_t p
 int rtdd_paint(rtdd_ctx *ctx, int x, int y, int scribbleColor, int scribbleRadius,
                uint8_t *edited, size_t editedPitch, uint8_t *scribble, size_t scribblePitch, int rows, int cols);
 
+/* replaces the host loop that turns a loaded annotation into the two planes the solver works on
+ * ref: src/main.cpp:160-170 (and :158 edited = the image, :132 scribble = 0).  `annotation` is ONE u8 plane, 32 = not annotated:
+ * every pixel != 32 gets edited B = G = R = that value and scribble = 255, every other pixel edited = bgr and scribble = 0.
+ * All four planes are device planes and must not overlap. */
+int rtdd_annotation_ingest(rtdd_ctx *ctx, const uint8_t *annotation, size_t annotationPitch, const uint8_t *bgr, size_t bgrPitch,
+                           uint8_t *edited, size_t editedPitch, uint8_t *scribble, size_t scribblePitch, int rows, int cols);
+
 /* ---- GPUDepthEffect ------------------------------------------------------ */
 
 /* replaces GPUSimulateDesaturation  ref: include/GPUDepthEffect.h:6-7, src/GPUDepthEffect.cu:8-27,95-103 */
@@ -241,6 +252,14 @@ int rtdd_frame_set_image(rtdd_ctx *ctx, const uint8_t *bgrHost, size_t bgrPitch)
 int rtdd_frame_solve_host(rtdd_ctx *ctx, const uint8_t *scribbleHost, size_t scribblePitch,
                           const uint8_t *editedHost, size_t editedPitch,
                           int maxIterations, uint8_t *depthU8Host, size_t depthU8Pitch);
+/* The same frame from the reference's persistent annotation format (the -a file, ref: src/main.cpp:160-170): ONE u8 HOST plane,
+ * 32 = not annotated.  Uploads 1 B/px instead of 4 B/px and expands it on the device (rtdd_annotation_ingest) into the
+ * context's level-0 scribble / edited planes; otherwise identical to rtdd_frame_solve_host. */
+int rtdd_frame_solve_host_annotation(rtdd_ctx *ctx, const uint8_t *annotationHost, size_t annotationPitch, int maxIterations,
+                                     uint8_t *depthU8Host, size_t depthU8Pitch);
+/* ref: src/main.cpp:291 -- download of the 8-bit depth map of the last solved frame into HOST memory.  sync = 0 leaves the copy
+ * in flight on the context stream (batch mode: one host thread keeps several contexts busy and synchronises them later). */
+int rtdd_frame_read_depth_u8(rtdd_ctx *ctx, uint8_t *depthU8Host, size_t depthU8Pitch, int sync);
 /* Same frame with the annotation planes already on the device (paint with
  * rtdd_frame_paint); nothing crosses PCIe. */
 int rtdd_frame_solve(rtdd_ctx *ctx, int maxIterations);

@@ -10,6 +10,23 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
+_PKG = os.path.join(os.path.dirname(_HERE), "realtimedepthdiffusion_b200")
+
+
+def pkg_file(name):
+    """A native-free module of the product package (refnames, planes, synth) loaded BY PATH: importing the package itself
+    dlopens librtdd.so, which the reference arm of bench.py must not have in its process."""
+    import importlib.util
+    import sys
+    key = "_rtdd_byPath_" + name
+    if key in sys.modules:
+        return sys.modules[key]
+    spec = importlib.util.spec_from_file_location(key, os.path.join(_PKG, name + ".py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[key] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
 LIBORACLE = os.path.join(_HERE, "liboracle.so")
 LIBREF = os.path.join(_HERE, "_ref", "libref.so")
 
@@ -260,6 +277,5 @@ def ref_api():
     if _ref is None:
         if not os.path.exists(LIBREF):
             raise ImportError("oracle/_ref/libref.so missing (built from /root/reference by realtimedepthdiffusion_b200/build.py)")
-        from realtimedepthdiffusion_b200._native import bind_reference_api
-        _ref = bind_reference_api(C.CDLL(LIBREF, mode=os.RTLD_LOCAL | os.RTLD_NOW))
+        _ref = pkg_file("refnames").bind_reference_api(C.CDLL(LIBREF, mode=os.RTLD_LOCAL | os.RTLD_NOW))
     return _ref

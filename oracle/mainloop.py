@@ -14,7 +14,8 @@ import numpy as np
 import torch
 
 from oracle import binding as ob
-from realtimedepthdiffusion_b200.api import pitched_empty
+
+pitched_empty = ob.pkg_file("planes").pitched_empty
 
 
 def ptr(t):

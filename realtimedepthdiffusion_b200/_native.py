@@ -70,50 +70,15 @@ SIGNATURES = {
     "rtdd_frame_set_image": (i32, [vp, vp, sz]),
     "rtdd_frame_solve_host": (i32, [vp, vp, sz, vp, sz, i32, vp, sz]),
     "rtdd_frame_solve": (i32, [vp, i32]),
+    "rtdd_frame_read_depth_u8": (i32, [vp, vp, sz, i32]),
+    "rtdd_frame_solve_host_annotation": (i32, [vp, vp, sz, i32, vp, sz]),
+    "rtdd_annotation_ingest": (i32, [vp, vp, sz, vp, sz, vp, sz, vp, sz, i32, i32]),
     "rtdd_frame_paint": (i32, [vp, i32, i32, i32, i32]),
     "rtdd_frame_plane": (i32, [vp, i32, i32, C.POINTER(vp), C.POINTER(sz), C.POINTER(i32), C.POINTER(i32)]),
     "rtdd_frame_effects": (i32, [vp, vp, sz, vp, sz, vp, sz]),
 }
 
-# the reference-named C++ shims (Itanium-mangled), same ten functions as include/GPU*.h
-SHIM_SYMBOLS = {
-    "GPUAllocateDeviceMemory": "_Z23GPUAllocateDeviceMemoryiii",
-    "GPUFreeDeviceMemory": "_Z19GPUFreeDeviceMemoryi",
-    "GPULoadWeights": "_Z14GPULoadWeightsf",
-    "GPUMatrixFreeSolver": "_Z19GPUMatrixFreeSolverPfmPhmS0_miififi",
-    "GPUConvertToFloat": "_Z17GPUConvertToFloatPhmPfmS_mii",
-    "GPUPyrDownAnnotation": "_Z20GPUPyrDownAnnotationPhmS_miiS_mS_mii",
-    "GPUPaintImage": "_Z13GPUPaintImageiiiiPhmS_mii",
-    "GPUSimulateDefocus": "_Z18GPUSimulateDefocusPhmPfmS_mii",
-    "GPUSimulateDesaturation": "_Z23GPUSimulateDesaturationPhmS_mPfmS_mii",
-    "GPUSimulateHaze": "_Z15GPUSimulateHazePhmPfmS_mii",
-}
-
-SHIM_SIGNATURES = {
-    "GPUAllocateDeviceMemory": [i32, i32, i32],
-    "GPUFreeDeviceMemory": [i32],
-    "GPULoadWeights": [f32],
-    "GPUMatrixFreeSolver": [vp, sz, vp, sz, vp, sz, i32, i32, f32, i32, f32, i32],
-    "GPUConvertToFloat": [vp, sz, vp, sz, vp, sz, i32, i32],
-    "GPUPyrDownAnnotation": [vp, sz, vp, sz, i32, i32, vp, sz, vp, sz, i32, i32],
-    "GPUPaintImage": [i32, i32, i32, i32, vp, sz, vp, sz, i32, i32],
-    "GPUSimulateDefocus": [vp, sz, vp, sz, vp, sz, i32, i32],
-    "GPUSimulateDesaturation": [vp, sz, vp, sz, vp, sz, vp, sz, i32, i32],
-    "GPUSimulateHaze": [vp, sz, vp, sz, vp, sz, i32, i32],
-}
-
-
-def bind_reference_api(cdll):
-    """Return {name: callable} for the ten reference-named functions of `cdll`
-    (works for librtdd.so's shims and for oracle/_ref/libref.so alike)."""
-    out = {}
-    for name, sym in SHIM_SYMBOLS.items():
-        fn = getattr(cdll, sym)
-        fn.restype = None
-        fn.argtypes = SHIM_SIGNATURES[name]
-        out[name] = fn
-    return out
-
+from .refnames import SHIM_SIGNATURES, SHIM_SYMBOLS, bind_reference_api  # noqa: E402,F401
 
 for _name, (_res, _args) in SIGNATURES.items():
     _fn = getattr(lib, _name)

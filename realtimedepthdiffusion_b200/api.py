@@ -33,29 +33,7 @@ def level_sizes(rows, cols, levels):
     return [(int(rows / 2.0 ** l), int(cols / 2.0 ** l)) for l in range(levels)]
 
 
-def pitched_empty(rows, cols, dtype, device, channels=1, align=512, fill=None):
-    """A rows x (cols*channels) plane whose row pitch is a multiple of `align` bytes,
-    like cv::cuda::GpuMat / cudaMallocPitch.  Returns a strided view; .stride(0)*itemsize is the pitch."""
-    item = torch.empty((), dtype=dtype).element_size()
-    row_bytes = cols * channels * item
-    pitch = (row_bytes + align - 1) // align * align
-    if rows == 0 or cols == 0:
-        return torch.empty((rows, cols * channels), dtype=dtype, device=device)
-    base = torch.empty((rows, pitch // item), dtype=dtype, device=device)
-    if fill is not None:
-        base.fill_(fill)
-    return base[:, : cols * channels]
-
-
-def to_dev(a, channels=1, device="cuda"):
-    """numpy [rows, cols(, channels)] -> pitched device plane [rows, cols * channels] (tools, tests)."""
-    import numpy as np
-    a = np.ascontiguousarray(a)
-    rows, cols = a.shape[:2]
-    dt = torch.from_numpy(a.reshape(rows, -1))
-    out = pitched_empty(rows, cols, dt.dtype, device, channels=channels)
-    out.copy_(dt)
-    return out
+from .planes import pitched_empty, to_dev  # noqa: E402,F401
 
 
 def _ptr(t):
@@ -227,13 +205,21 @@ class DepthDiffusion:
         self._ck(lib.rtdd_quantise_u8(self._h, _ptr(src), _pitch(src), _ptr(dst), _pitch(dst), rows, cols))
 
     # -- whole frame (main.cpp:232-295) -----------------------------------------------
-    def frame_set_image(self, bgr_host):
-        """bgr_host: uint8 numpy array or CPU tensor, rows x cols x 3, C-contiguous."""
+    def frame_set_image(self, bgr_host, sync=True):
+        """bgr_host: uint8 numpy array or CPU tensor, rows x cols x 3, C-contiguous.  sync=False leaves the upload and the
+        gray pyramid in flight on the context stream (the caller keeps bgr_host alive and unchanged until it synchronises)."""
         t = torch.as_tensor(bgr_host)
         assert t.dtype == torch.uint8 and tuple(t.shape) == (self.rows, self.cols, 3) and t.is_contiguous()
         self._keep_bgr = t
         self._ck(lib.rtdd_frame_set_image(self._h, C.c_void_p(t.data_ptr()), self.cols * 3))
-        self.sync()
+        if sync:
+            self.sync()
+
+    def frame_read_depth_u8(self, depth_u8_host, sync=True):
+        d = torch.as_tensor(depth_u8_host)
+        assert d.dtype == torch.uint8 and tuple(d.shape) == (self.rows, self.cols) and d.is_contiguous()
+        self._ck(lib.rtdd_frame_read_depth_u8(self._h, C.c_void_p(d.data_ptr()), self.cols, 1 if sync else 0))
+        return d
 
     def frame_solve_host(self, scribble_host, edited_host, max_iterations=1000, depth_u8_host=None):
         s = torch.as_tensor(scribble_host)
@@ -247,6 +233,24 @@ class DepthDiffusion:
         self._ck(lib.rtdd_frame_solve_host(self._h, C.c_void_p(s.data_ptr()), self.cols, C.c_void_p(e.data_ptr()), self.cols * 3,
                                            int(max_iterations), C.c_void_p(d.data_ptr()) if d is not None else C.c_void_p(0), self.cols))
         return d
+
+    def frame_solve_host_annotation(self, annotation_host, max_iterations=1000, depth_u8_host=None):
+        """One frame from the reference's annotation format (ONE u8 plane, 32 = not annotated; ref: src/main.cpp:160-170)."""
+        a = torch.as_tensor(annotation_host)
+        assert a.dtype == torch.uint8 and tuple(a.shape) == (self.rows, self.cols) and a.is_contiguous()
+        d = depth_u8_host
+        if d is not None:
+            d = torch.as_tensor(d)
+            assert d.dtype == torch.uint8 and tuple(d.shape) == (self.rows, self.cols) and d.is_contiguous()
+        self._ck(lib.rtdd_frame_solve_host_annotation(self._h, C.c_void_p(a.data_ptr()), self.cols, int(max_iterations),
+                                                      C.c_void_p(d.data_ptr()) if d is not None else C.c_void_p(0), self.cols))
+        return d
+
+    def annotation_ingest(self, annotation, bgr, edited, scribble):
+        """Device planes: annotation [rows, cols] u8, bgr / edited [rows, 3*cols] u8, scribble [rows, cols] u8."""
+        rows, cols = scribble.shape
+        self._ck(lib.rtdd_annotation_ingest(self._h, _ptr(annotation), _pitch(annotation), _ptr(bgr), _pitch(bgr), _ptr(edited), _pitch(edited),
+                                            _ptr(scribble), _pitch(scribble), rows, cols))
 
     def frame_solve(self, max_iterations=1000):
         self._ck(lib.rtdd_frame_solve(self._h, int(max_iterations)))

@@ -65,6 +65,65 @@ cudaError_t launch_convert(cudaStream_t s, const uint8_t *src, size_t srcPitch, 
 }
 
 // ---------------------------------------------------------------------------
+// annotation ingest: the reference's persistent annotation format is ONE gray plane, 32 = "not annotated"
+// (the -a file, ref: src/main.cpp:160-170):  every pixel != 32 gets edited BGR := that value and scribble := 255;
+// all other pixels keep the original image in `edited` (src/main.cpp:158) and 0 in `scribble` (:132).
+// One thread = 4 pixels: 4 B of annotation + 12 B of image in, 12 B + 4 B out.  A frame that arrives from the host needs
+// only this plane (1 B/px) instead of the scribble + 3-channel edited planes (4 B/px) main.cpp uploads (:236-237).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+annotation_ingest_kernel(const uint8_t *__restrict__ ann, size_t annPitch, const uint8_t *__restrict__ bgr, size_t bgrPitch,
+                         uint8_t *__restrict__ edited, size_t editedPitch, uint8_t *__restrict__ scribble, size_t scribblePitch,
+                         int rows, int cols, int vec)
+{
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x4 >= cols || y >= rows) return;
+    const uint8_t *aRow = ann + (size_t)y * annPitch + x4;
+    const uint8_t *bRow = bgr + (size_t)y * bgrPitch + 3 * x4;
+    uint8_t *eRow = edited + (size_t)y * editedPitch + 3 * x4;
+    uint8_t *sRow = scribble + (size_t)y * scribblePitch + x4;
+    if (vec && x4 + 4 <= cols) {
+        const unsigned int a = __ldg((const unsigned int *)aRow);
+        unsigned int w[3] = {__ldg((const unsigned int *)bRow), __ldg((const unsigned int *)bRow + 1), __ldg((const unsigned int *)bRow + 2)};
+        unsigned int m = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const unsigned int v = (a >> (8 * i)) & 0xFFu;
+            if (v != 32u) {
+                m |= 0xFFu << (8 * i);
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    const int b = 3 * i + c;                       // byte index inside the 12-byte group
+                    w[b >> 2] = (w[b >> 2] & ~(0xFFu << (8 * (b & 3)))) | (v << (8 * (b & 3)));
+                }
+            }
+        }
+        ((unsigned int *)eRow)[0] = w[0]; ((unsigned int *)eRow)[1] = w[1]; ((unsigned int *)eRow)[2] = w[2];
+        *(unsigned int *)sRow = m;
+    } else {
+        for (int i = 0; x4 + i < cols; i++) {
+            const unsigned int v = __ldg(aRow + i);
+            const bool on = (v != 32u);
+            for (int c = 0; c < 3; c++) eRow[3 * i + c] = on ? (uint8_t)v : __ldg(bRow + 3 * i + c);
+            sRow[i] = on ? 255 : 0;
+        }
+    }
+}
+
+cudaError_t launch_annotation_ingest(cudaStream_t s, const uint8_t *ann, size_t annPitch, const uint8_t *bgr, size_t bgrPitch,
+                                     uint8_t *edited, size_t editedPitch, uint8_t *scribble, size_t scribblePitch, int rows, int cols)
+{
+    const int vec = ((((uintptr_t)ann | annPitch | (uintptr_t)bgr | bgrPitch | (uintptr_t)edited | editedPitch | (uintptr_t)scribble | scribblePitch) & 3u) == 0) ? 1 : 0;
+    dim3 block(64, 4);
+    dim3 grid(rtdd_div_up(rtdd_div_up(cols, 4), block.x), rtdd_div_up(rows, block.y));
+    return launch_pdl(annotation_ingest_kernel, grid, block, (size_t)0, s, ann, annPitch, bgr, bgrPitch, edited, editedPitch, scribble, scribblePitch,
+                      rows, cols, vec);
+}
+
+// ---------------------------------------------------------------------------
 // annotation restriction.  The reference scans rows {2y-1, 2y} x cols {2x-1, 2x}
 // in row-major order and lets every scribbled hit overwrite the output, so the
 // winner is the LAST hit: (2y,2x) > (2y,2x-1) > (2y-1,2x) > (2y-1,2x-1).

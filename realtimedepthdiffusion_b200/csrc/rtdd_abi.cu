@@ -570,6 +570,13 @@ int rtdd_set_tuning(rtdd_ctx *ctx, const char *key, int value)
         destroy_graphs(ctx);
         return 0;
     }
+    if (strcmp(key, "blocked_grid_cap") == 0 && value >= 0) {
+        rtdd::set_blocked_grid_cap(value);
+        DeviceGuard guard(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+        destroy_graphs(ctx);
+        return 0;
+    }
     if (strcmp(key, "blocked_tma") == 0 && (value == 0 || value == 1)) {
         rtdd::set_blocked_tma(value);
         DeviceGuard guard(ctx->device);
@@ -1069,6 +1076,19 @@ int rtdd_paint(rtdd_ctx *ctx, int x, int y, int scribbleColor, int scribbleRadiu
     return 0;
 }
 
+int rtdd_annotation_ingest(rtdd_ctx *ctx, const uint8_t *annotation, size_t annotationPitch, const uint8_t *bgr, size_t bgrPitch,
+                           uint8_t *edited, size_t editedPitch, uint8_t *scribble, size_t scribblePitch, int rows, int cols)
+{
+    if (!ctx) return RTDD_E_ARG;
+    if (!annotation || !bgr || !edited || !scribble || rows < 0 || cols < 0) return rtdd_fail(ctx, RTDD_E_ARG, "rtdd_annotation_ingest");
+    if (rows == 0 || cols == 0) return 0;
+    DeviceGuard guard(ctx->device);
+    RTDD_TRY(rtdd::launch_annotation_ingest(ctx->stream, annotation, annotationPitch, bgr, bgrPitch, edited, editedPitch, scribble, scribblePitch, rows, cols),
+             "rtdd_annotation_ingest");
+    ctx->launches++;
+    return 0;
+}
+
 // ---- GPUDepthEffect ------------------------------------------------------------
 
 int rtdd_desaturate(rtdd_ctx *ctx, const uint8_t *orig, size_t origPitch, const uint8_t *gray, size_t grayPitch,
@@ -1206,7 +1226,8 @@ static int frame_alloc(rtdd_ctx *ctx)
     }
     ctx->bgrPitch = rtdd_round_up((size_t)ctx->cols * 3, 512);
     ctx->depthU8Pitch = rtdd_round_up((size_t)ctx->cols, 512);
-    total += ctx->bgrPitch * ctx->rows + ctx->depthU8Pitch * ctx->rows;
+    ctx->annotPitch = ctx->depthU8Pitch;
+    total += ctx->bgrPitch * ctx->rows + ctx->depthU8Pitch * ctx->rows + ctx->annotPitch * ctx->rows;
     RTDD_TRY(cudaMalloc(&ctx->frameArena, total), "frame arena");
     char *p = (char *)ctx->frameArena;
     for (int l = 0; l < ctx->levels; l++) {
@@ -1217,7 +1238,8 @@ static int frame_alloc(rtdd_ctx *ctx)
         F.edited = (uint8_t *)p; p += F.editedPitch * F.rows;
     }
     ctx->bgr = (uint8_t *)p; p += ctx->bgrPitch * ctx->rows;
-    ctx->depthU8 = (uint8_t *)p;
+    ctx->depthU8 = (uint8_t *)p; p += ctx->depthU8Pitch * ctx->rows;
+    ctx->annot = (uint8_t *)p;
     return 0;
 }
 
@@ -1345,6 +1367,49 @@ int rtdd_frame_solve_host(rtdd_ctx *ctx, const uint8_t *scribbleHost, size_t scr
                  "rtdd_frame_solve_host (download)");                          // main.cpp:291
         RTDD_TRY(cudaStreamSynchronize(s), "rtdd_frame_solve_host");
     }
+    return 0;
+}
+
+// The same frame fed with the reference's persistent annotation format (ref: src/main.cpp:160-170): ONE gray plane, 32 = not
+// annotated.  1 B/px crosses PCIe instead of the 4 B/px of scribble + 3-channel edited; the expansion main.cpp does on
+// the host runs on the device (annotation_ingest_kernel).  Results are identical to rtdd_frame_solve_host on the planes
+// main.cpp would have derived from the same annotation.
+int rtdd_frame_solve_host_annotation(rtdd_ctx *ctx, const uint8_t *annotationHost, size_t annotationPitch, int maxIterations,
+                                     uint8_t *depthU8Host, size_t depthU8Pitch)
+{
+    if (!ctx) return RTDD_E_ARG;
+    if (!ctx->imageSet) return rtdd_fail(ctx, RTDD_E_STATE, "rtdd_frame_solve_host_annotation");
+    if (!annotationHost || annotationPitch < (size_t)ctx->cols || (depthU8Host && depthU8Pitch < (size_t)ctx->cols))
+        return rtdd_fail(ctx, RTDD_E_ARG, "rtdd_frame_solve_host_annotation");
+    DeviceGuard guard(ctx->device);
+    cudaStream_t s = ctx->stream;
+    RtddFrameLevel &F = ctx->fl[0];
+    RTDD_TRY(cudaMemcpy2DAsync(ctx->annot, ctx->annotPitch, annotationHost, annotationPitch, (size_t)ctx->cols, ctx->rows, cudaMemcpyHostToDevice, s),
+             "rtdd_frame_solve_host_annotation (upload)");
+    RTDD_TRY(rtdd::launch_annotation_ingest(s, ctx->annot, ctx->annotPitch, ctx->bgr, ctx->bgrPitch, F.edited, F.editedPitch, F.scribble, F.scribblePitch,
+                                            ctx->rows, ctx->cols), "rtdd_frame_solve_host_annotation (ingest)");
+    ctx->launches++;
+    int rc = rtdd_frame_solve(ctx, maxIterations);
+    if (rc) return rc;
+    if (depthU8Host) {
+        RTDD_TRY(cudaMemcpy2DAsync(depthU8Host, depthU8Pitch, ctx->depthU8, ctx->depthU8Pitch, (size_t)ctx->cols, ctx->rows, cudaMemcpyDeviceToHost, s),
+                 "rtdd_frame_solve_host_annotation (download)");
+        RTDD_TRY(cudaStreamSynchronize(s), "rtdd_frame_solve_host_annotation");
+    }
+    return 0;
+}
+
+// The 8-bit depth map of the last solved frame -> HOST (ref: src/main.cpp:291 download).  sync = 0 leaves the copy in flight on the
+// context stream (the caller synchronises later: several contexts' frames then overlap from one host thread).
+int rtdd_frame_read_depth_u8(rtdd_ctx *ctx, uint8_t *depthU8Host, size_t depthU8Pitch, int sync)
+{
+    if (!ctx) return RTDD_E_ARG;
+    if (!ctx->imageSet) return rtdd_fail(ctx, RTDD_E_STATE, "rtdd_frame_read_depth_u8");
+    if (!depthU8Host || depthU8Pitch < (size_t)ctx->cols) return rtdd_fail(ctx, RTDD_E_ARG, "rtdd_frame_read_depth_u8");
+    DeviceGuard guard(ctx->device);
+    RTDD_TRY(cudaMemcpy2DAsync(depthU8Host, depthU8Pitch, ctx->depthU8, ctx->depthU8Pitch, (size_t)ctx->cols, ctx->rows, cudaMemcpyDeviceToHost, ctx->stream),
+             "rtdd_frame_read_depth_u8");
+    if (sync) RTDD_TRY(cudaStreamSynchronize(ctx->stream), "rtdd_frame_read_depth_u8");
     return 0;
 }
 

@@ -105,6 +105,7 @@ struct rtdd_ctx {
     void *frameArena = nullptr;
     uint8_t *bgr = nullptr; size_t bgrPitch = 0;
     uint8_t *depthU8 = nullptr; size_t depthU8Pitch = 0;
+    uint8_t *annot = nullptr; size_t annotPitch = 0;      // level-0 single-plane annotation staging (rtdd_frame_solve_host_annotation)
     bool imageSet = false;
     bool stripResidual = false;        // rtdd_strip_pass also fills the level's residual word (+7 % per pass at 16K: only rtdd_solve_level_converge asks)
     bool peerStaging = false;          // rtdd_set_tuning("strip_peer_staging", 1): halo rows travel through rtdd_strip_push / _pull
@@ -182,6 +183,7 @@ cudaError_t configure_kernels();
 int blocked_max_T();
 void set_blocked_tile_override(int tile);
 void set_blocked_tma(int enabled);
+void set_blocked_grid_cap(int cap);
 void set_resident_warps(int w);
 void set_resident_r1_max_warps(int w);
 void set_pdl(int on);
@@ -220,6 +222,8 @@ cudaError_t launch_pyrdown_annotation(cudaStream_t s, const uint8_t *prevScribbl
                                       const uint8_t *prevEdited, size_t prevEditedPitch, int previousRows, int previousCols,
                                       uint8_t *currScribble, size_t currScribblePitch, uint8_t *currEdited, size_t currEditedPitch,
                                       int currentRows, int currentCols);
+cudaError_t launch_annotation_ingest(cudaStream_t s, const uint8_t *ann, size_t annPitch, const uint8_t *bgr, size_t bgrPitch,
+                                     uint8_t *edited, size_t editedPitch, uint8_t *scribble, size_t scribblePitch, int rows, int cols);
 cudaError_t launch_paint(cudaStream_t s, int x, int y, int color, int radius, uint8_t *edited, size_t editedPitch,
                          uint8_t *scribble, size_t scribblePitch, int rows, int cols, int *launched);
 cudaError_t launch_bgr2gray(cudaStream_t s, const uint8_t *bgr, size_t bgrPitch, uint8_t *gray, size_t grayPitch, int rows, int cols);

@@ -81,3 +81,9 @@ def synth_case(rows, cols, seed, strokes=None, coverage=0.10):
     ev = brush_events(rows, cols, seed, strokes, steps)
     scribble, edited = paint_events(bgr, ev)
     return bgr, scribble, edited
+
+
+def annotation_plane(scribble, edited):
+    """The single-plane annotation main.cpp would have loaded to arrive at (scribble, edited): the painted value where
+    scribble == 255, 32 elsewhere (ref: src/main.cpp:160-170; none of the paintable depths is 32)."""
+    return np.where(scribble == 255, edited[..., 0], 32).astype(np.uint8)

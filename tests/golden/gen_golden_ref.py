@@ -123,9 +123,40 @@ def weights_case(api, libref, rows, cols, seed, levels, level):
     return {"gray": gray, "depth": depth, "int2": idx.cpu().numpy(), "level": np.int32(level), "levels": np.int32(levels)}
 
 
+def dataset_goldens(api):
+    """All 12 dataset pairs (BASELINE configs[0]) through the reference's own kernels, native resolution, 1000 sweeps at the
+    coarsest level: per-level sha256 of the fp32 outputs, sha of the u8 map, and the same for a second frame with one more
+    stroke (state carried over).  Hashes only -- the inputs are in tests/golden/dataset_pack.npz."""
+    import json
+    from tests import dataset
+    out = {}
+    for name in dataset.NAMES:
+        bgr, scribble, edited, _ = dataset.load_pair(name)
+        loop = MainLoop(api, bgr)
+        u8 = loop.frame(scribble, edited, 1000, keep_levels=True)
+        rec = {"rows": loop.rows, "cols": loop.cols, "levels": loop.levels, "sizes": [list(x) for x in loop.sizes],
+               "out_sha": {str(l): sha(d["out"]) for l, d in loop.per_level.items()},
+               "in_sha": {str(l): sha(d["in"]) for l, d in loop.per_level.items()},
+               "depth_u8_sha": sha(u8), "depth_u8_sample": u8[::64, ::64].tolist()}
+        ev = synth.brush_events(loop.rows, loop.cols, 99, 1, 6)
+        s2, e2 = synth.paint_events(bgr, ev, scribble.copy(), edited.copy())
+        u8b = loop.frame(s2, e2, 1000, keep_levels=True)
+        rec["frame2_out_sha_0"] = sha(loop.per_level[0]["out"])
+        rec["frame2_depth_u8_sha"] = sha(u8b)
+        loop.close()
+        out[name] = rec
+        print("dataset", name, loop.cols, "x", loop.rows, "levels", loop.levels, flush=True)
+    with open(os.path.join(OUT, "ref_dataset.json"), "w") as f:
+        json.dump(out, f, indent=1, sort_keys=True)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     api = ob.ref_api()
+    if "--dataset" in sys.argv:
+        dataset_goldens(api)
+        print("golden written to", OUT)
+        return
     libref = C.CDLL(ob.LIBREF)    # same handle dlopen returns again (already loaded)
     dog = None
     only = sys.argv[1:]

@@ -176,6 +176,36 @@ def test_oracle_reproduces_reference_solver_golden(name):
     assert (u8b == z["frame2_depth_u8"]).all()
 
 
+def _dataset_golden():
+    import json
+    path = os.path.join(GOLD, "ref_dataset.json")
+    if not os.path.exists(path):
+        pytest.skip("tests/golden/ref_dataset.json missing (tests/golden/gen_golden_ref.py --dataset on a GPU box)")
+    return json.load(open(path))
+
+
+@pytest.mark.parametrize("name", ["arara", "archespark", "dog", "flower", "heidelberg", "hills", "pigs", "rock", "straw", "streetart",
+                                  "vintagegirl", "womanparasol"])
+def test_oracle_reproduces_reference_on_every_dataset_pair(name):
+    """BASELINE configs[0], all 12 pairs: 4- and 5-level pyramids, ten of them with floor/ceil size mismatches between levels
+    (SURVEY.md Appendix B); the hashes were recorded from the reference's own kernels on a B200."""
+    from tests import dataset
+    gold = _dataset_golden()[name]
+    bgr, scribble, edited, _ = dataset.load_pair(name)
+    st = ob.FrameState(bgr)
+    assert st.levels == gold["levels"] and (st.rows, st.cols) == (gold["rows"], gold["cols"])
+    u8 = st.solve(scribble, edited, 1000, keep_levels=True)
+    for l in range(st.levels - 1, -1, -1):
+        assert sha(st.per_level[l]["in"]) == gold["in_sha"][str(l)], "level %d input" % l
+        assert sha(st.per_level[l]["out"]) == gold["out_sha"][str(l)], "level %d output" % l
+    assert sha(u8) == gold["depth_u8_sha"]
+    ev = synth.brush_events(st.rows, st.cols, 99, 1, 6)
+    s2, e2 = synth.paint_events(bgr, ev, scribble.copy(), edited.copy())
+    u8b = st.solve(s2, e2, 1000, keep_levels=True)
+    assert sha(st.per_level[0]["out"]) == gold["frame2_out_sha_0"]
+    assert sha(u8b) == gold["frame2_depth_u8_sha"]
+
+
 def test_oracle_reproduces_reference_weights_golden():
     for f in _golden("ref_weights_*.npz"):
         z = np.load(f)

@@ -22,51 +22,8 @@ from realtimedepthdiffusion_b200.api import pitched_empty     # noqa: E402
 
 
 def synth_on_device(rows, cols, seed, ctx, coverage=0.10):
-    """Counter-seeded synthetic image + brush scribbles generated ON the device (identical on every rank)."""
-    dev = ctx.device
-    g = torch.Generator(device=dev)
-    g.manual_seed(seed)
-    rng = np.random.default_rng(seed)
-    bgr = pitched_empty(rows, cols, torch.uint8, dev, channels=3)
-    img = bgr.view(torch.uint8)
-    base = rng.integers(0, 256, 3)
-    v = img[:, : cols * 3].view(rows, cols, 3) if img.stride(0) == cols * 3 else None
-    plane = torch.empty((rows, cols, 3), dtype=torch.uint8, device=dev)
-    plane[:] = torch.tensor(base, dtype=torch.uint8, device=dev)
-    for _ in range(64):
-        cy, cx = rng.uniform(0, rows), rng.uniform(0, cols)
-        hy, hx = rng.uniform(0.03, 0.25) * rows, rng.uniform(0.03, 0.25) * cols
-        colour = torch.tensor(rng.integers(0, 256, 3), dtype=torch.uint8, device=dev)
-        y0, y1 = max(int(cy - hy), 0), min(int(cy + hy) + 1, rows)
-        x0, x1 = max(int(cx - hx), 0), min(int(cx + hx) + 1, cols)
-        if y1 <= y0 or x1 <= x0:
-            continue
-        if rng.random() < 0.5:
-            plane[y0:y1, x0:x1] = colour
-        else:
-            yy = (torch.arange(y0, y1, device=dev, dtype=torch.float32)[:, None] - cy) / hy
-            xx = (torch.arange(x0, x1, device=dev, dtype=torch.float32)[None, :] - cx) / hx
-            m = (yy * yy + xx * xx) <= 1.0
-            sub = plane[y0:y1, x0:x1]
-            sub[m] = colour
-    step = max(1, (1 << 24) // cols)
-    for r0 in range(0, rows, step):                             # noise in row chunks (bounded temporaries)
-        r1 = min(rows, r0 + step)
-        n = torch.randn((r1 - r0, cols, 1), generator=g, device=dev) * 4.0
-        plane[r0:r1] = (plane[r0:r1].float() + n).round_().clamp_(0, 255).to(torch.uint8)
-    bgr.copy_(plane.view(rows, cols * 3))
-    del plane
-    scribble = pitched_empty(rows, cols, torch.uint8, dev, fill=0)
-    edited = pitched_empty(rows, cols, torch.uint8, dev, channels=3)
-    edited.copy_(bgr)
-    radius = int(min(rows, cols) * 0.02)
-    side = 2 * (radius // 2) + 1
-    per_stroke = side * side + 23 * side * max(radius * 0.6, 1.0)
-    nstrokes = max(int(coverage * rows * cols / per_stroke), 2)
-    for (x, y, colour, rad) in synth.brush_events(rows, cols, seed, nstrokes, 24):
-        ctx.paint_image(x, y, colour, rad, edited, scribble)    # the reference's brush (GPUPaintImage)
-    ctx.sync()
-    return bgr, scribble, edited
+    from realtimedepthdiffusion_b200 import synth_device
+    return synth_device.synth_case_device(rows, cols, seed, ctx, coverage)
 
 
 def main():
