@@ -123,7 +123,9 @@ int rtdd_selftest_division(rtdd_ctx *ctx, unsigned long long n, unsigned long lo
 int rtdd_set_sweep_variant(rtdd_ctx *ctx, int variant, int sweepsPerPass);
 /* Process-wide tuning knobs for experiments (tools/tune_blocked.py); results never change, only speed.
  * "blocked_tile": 0 auto, 64 = 128x64-pixel regions, 34 = 128x32 regions with 2 rows per warp, 32 = 128x32 with 4 rows per warp;
- * "blocked_tma": 1 (default) TMA-fed persistent form of the 128x64 kernel, 0 = plain LDG form;
+ * "blocked_tma": 2 (default) TMA-fed persistent thread-block clusters (vertically adjacent CTAs share their edge rows over
+ *                distributed shared memory), 1 = TMA-fed persistent single CTAs, 0 = plain LDG form;
+ * "blocked_cluster": CTAs per cluster of the default form (1, 2 (default), 4, 8);
  * "blocked_grid_cap": > 0 limits the persistent form to that many CTAs (tests: every CTA then walks several regions even on
  *                     small levels, so the region loop -- phase flips, re-issue under the sweeps -- is checked against the oracle);
  * "spin_timeout_ms": device-time limit of a halo wait on a neighbouring rank (default 20000, 0 = for ever); a wait that gives

@@ -93,6 +93,7 @@ void build_tensor_maps(rtdd_ctx *ctx)
         ok = ok && encode_plane_map(fn, &L.tmLinkR, L.linkR, false, L.pitchB, L.rows, 144, 64);
         ok = ok && encode_plane_map(fn, &L.tmLinkD, L.linkD, false, L.pitchB, L.rows, 144, 64);
         ok = ok && encode_plane_map(fn, &L.tmMask, L.mask, false, L.pitchB, L.rows, 144, 64);
+        ok = ok && encode_plane_map(fn, &L.tmLinkD1, L.linkD, false, L.pitchB, L.rows, 144, 65);
         L.hasMaps = ok;
     }
 }
@@ -212,6 +213,7 @@ struct LevelArgs {
     // values re-injected from `edited`; it is produced inside the level set-up instead of being read from `depth`
     const float *coarse; size_t coarsePitch; int coarseRows, coarseCols;
     const uint8_t *edited; size_t editedPitch;
+    bool resetBad;                        // clear the level's out-of-range flag first (the whole-frame graph clears all levels' flags at its start)
 };
 
 // Opt-in (rtdd_set_tuning("fused_prolong", 1)): bit-identical and tested, but measured no faster than the three separate
@@ -228,6 +230,7 @@ int enqueue_level(rtdd_ctx *ctx, cudaStream_t s, const LevelArgs &a, bool captur
     const int threshold = (a.level == 0) ? 0 : 4;          // ref: src/GPUSolver.cu:201-202
     int n = 0;
     unsigned int *resetResidual = (a.iters > 0) ? L.dResidual : nullptr;     // the set-up kernel zeroes the level's residual word
+    if (a.resetBad) RTDD_TRY(cudaMemsetAsync(L.dBad, 0, sizeof(unsigned int), s), "level flags");
     if (a.coarse) {
         // ref: src/main.cpp:272-281 + src/GPUSolver.cu:290-293 in one pass; the guess itself is never stored as a pitched plane
         RTDD_TRY(rtdd::launch_level_prolong_init(s, L, a.coarse, a.coarsePitch, a.coarseRows, a.coarseCols, a.edited, a.editedPitch,
@@ -438,6 +441,7 @@ int rtdd_create(int rows, int cols, int levels, int device, rtdd_ctx **out)
     for (int l = 0; l < levels; l++) {
         RtddLevel &L = ctx->lv[l];
         L.dResidual = resWords + l;
+        L.dBad = resWords + 32 + l;
         L.dStripWords = stripWords + 16 * l;
         for (int k = 0; k < 4; k++) { L.x[k] = (float *)p; p += rtdd_round_up((size_t)L.pitchF * L.rows * sizeof(float), 256); }
         L.linkR = (uint8_t *)p; p += rtdd_round_up((size_t)L.pitchB * L.rows, 256);
@@ -577,7 +581,14 @@ int rtdd_set_tuning(rtdd_ctx *ctx, const char *key, int value)
         destroy_graphs(ctx);
         return 0;
     }
-    if (strcmp(key, "blocked_tma") == 0 && (value == 0 || value == 1)) {
+    if (strcmp(key, "blocked_cluster") == 0 && (value == 1 || value == 2 || value == 4 || value == 8)) {
+        rtdd::set_blocked_cluster(value);
+        DeviceGuard guard(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+        destroy_graphs(ctx);
+        return 0;
+    }
+    if (strcmp(key, "blocked_tma") == 0 && value >= 0 && value <= 2) {
         rtdd::set_blocked_tma(value);
         DeviceGuard guard(ctx->device);
         cudaStreamSynchronize(ctx->stream);
@@ -607,6 +618,7 @@ static int edge_pass(rtdd_ctx *ctx, const float *depth, size_t depthPitch, const
     // ref: src/GPUSolver.cu:201-202 -- threshold 4, 0 at level 0; :196 -- ungated on the coarsest level
     const bool coarsest = (level == ctx->levels - 1);
     const int threshold = (level == 0) ? 0 : 4;
+    RTDD_TRY(cudaMemsetAsync(L.dBad, 0, sizeof(unsigned int), ctx->stream), where);
     RTDD_TRY(rtdd::launch_level_init(ctx->stream, L, depth, depthPitch, scribble, scribblePitch, gray, grayPitch, coarsest, threshold, L.x[0]), where);
     ctx->launches++;
     return 0;
@@ -630,7 +642,7 @@ int rtdd_solve_level(rtdd_ctx *ctx, float *depth, size_t depthPitch, const uint8
     key.kind = 1; key.level = level; key.iters = maxIterations; key.variant = variant; key.T = T;
     key.p[0] = depth; key.p[1] = scribble; key.p[2] = gray;
     key.pitch[0] = depthPitch; key.pitch[1] = scribblePitch; key.pitch[2] = grayPitch;
-    const LevelArgs args{level, maxIterations, depth, depthPitch, scribble, scribblePitch, gray, grayPitch, nullptr, 0, nullptr, 0, 0, 0, nullptr, 0};
+    const LevelArgs args{level, maxIterations, depth, depthPitch, scribble, scribblePitch, gray, grayPitch, nullptr, 0, nullptr, 0, 0, 0, nullptr, 0, true};
     return run_cached_graph(ctx, key, [&](cudaStream_t cs, int *kernels) { return enqueue_level(ctx, cs, args, true, kernels); });
 }
 
@@ -750,6 +762,7 @@ int rtdd_strip_init(rtdd_ctx *ctx, int level, const float *depth, size_t depthPi
     const float *d = (const float *)((const char *)depth + (size_t)winBegin * depthPitch);
     // the window's last row needs the gray/depth row below it only if that row is inside the window; a window edge
     // inside the image simply loses that link, which only affects rows that go stale anyway
+    RTDD_TRY(cudaMemsetAsync(L.dBad, 0, sizeof(unsigned int), ctx->stream), "rtdd_strip_init");
     RTDD_TRY(rtdd::launch_level_init(ctx->stream, W, d, depthPitch, scribble + (size_t)winBegin * scribblePitch, scribblePitch,
                                      gray + (size_t)winBegin * grayPitch, grayPitch, coarsest, threshold, L.x[0]), "rtdd_strip_init");
     ctx->launches++;
@@ -925,6 +938,7 @@ int rtdd_strip_pass(rtdd_ctx *ctx, int level, int firstSweep, int nsweeps, int h
     for (int i = 0; i < RTDD_MAX_T; i++) pack.w[i] = (i < nsweeps) ? om[firstSweep + i] : 0.0f;
     RtddLevel W = L;
     W.rows = L.stripRows;
+    W.magnitudeCheck = true;           // ghost rows arrive from other GPUs: every pass scans its own tiles (see sweep_cluster_kernel)
     const int src = L.stripPair, dst = src ^ 2;
     // on request, the residual of this pass's last sweep (over the whole window; stale ghost rows can only raise it).  Not by
     // default: measured on the 16K level-0 pass, accumulating it costs 4.14 vs 3.87 ms per pass (ncu launch lists,
@@ -1288,6 +1302,7 @@ static int frame_solve_from(rtdd_ctx *ctx, int maxIterations, int startLevel)
     return run_cached_graph(ctx, key, [&](cudaStream_t cs, int *kernels) -> int {
         const int Lc = startLevel;          // coarsest level that is (re)solved; it starts from its current depth plane
         int n = 0;
+        RTDD_TRY(cudaMemsetAsync(ctx->lv[0].dBad, 0, sizeof(unsigned int) * ctx->levels, cs), "frame: level flags");   // one node for all levels
         for (int l = 1; l <= Lc; l++) {                                       // main.cpp:249
             RtddFrameLevel &P = ctx->fl[l - 1], &F = ctx->fl[l];
             RTDD_TRY(rtdd::launch_pyrdown_annotation(cs, P.scribble, P.scribblePitch, P.edited, P.editedPitch, P.rows, P.cols,
@@ -1305,7 +1320,7 @@ static int frame_solve_from(rtdd_ctx *ctx, int maxIterations, int startLevel)
             const int iters = rtdd_level_iterations(maxIterations, ctx->levels, l);
             // level 0 also emits the 8-bit map (main.cpp:290) from its last sweep pass
             LevelArgs args{l, iters, F.depth, F.depthPitch, F.scribble, F.scribblePitch, F.gray, F.grayPitch,
-                           l == 0 ? ctx->depthU8 : nullptr, l == 0 ? ctx->depthU8Pitch : 0, nullptr, 0, 0, 0, nullptr, 0};
+                           l == 0 ? ctx->depthU8 : nullptr, l == 0 ? ctx->depthU8Pitch : 0, nullptr, 0, 0, 0, nullptr, 0, false};
             if (fuseNext) {
                 // this level's guess = prolongation of the level above + its own Dirichlet values, formed by its set-up kernel
                 RtddFrameLevel &C = ctx->fl[l + 1];

@@ -26,6 +26,7 @@ struct RtddLevel {
     uint8_t *mask = nullptr;   // 0xFF where the scribble plane == 255 (Dirichlet), else 0
     // TMA descriptors of the planes above (128x64-element boxes), built once in rtdd_create
     CUtensorMap tmX[4], tmLinkR, tmLinkD, tmMask;
+    CUtensorMap tmLinkD1;      // linkD as 144 x 65 boxes: the cluster form loads the row above its tile as well
     bool hasMaps = false;
     // events bracketing the most recent sweep graph of this level (rtdd_level_sweep_ms)
     cudaEvent_t evBegin = nullptr, evEnd = nullptr;
@@ -43,6 +44,9 @@ struct RtddLevel {
     float *stage = nullptr;
     unsigned int peerSeq = 0;              // exchanges done so far on this level (monotonic; identical on every rank)
     unsigned int *dResidual = nullptr;   // bits of the max-norm of the last sweep's update (rtdd_level_residual)
+    unsigned int *dBad = nullptr;        // != 0: the level's start iterate holds a value beyond +-4096 or a NaN (set by the level set-up kernel,
+                                         // cleared by a memset before it): the sweeps then divide the IEEE way
+    bool magnitudeCheck = false;         // row-strip windows: ghost rows come from other GPUs, so every pass scans its own tiles instead
 };
 
 // Context-owned images of the frame driver (what main.cpp keeps in GpuMat vectors).
@@ -182,7 +186,8 @@ cudaError_t launch_halo_wait(cudaStream_t s, const unsigned int *waitUp, const u
 cudaError_t configure_kernels();
 int blocked_max_T();
 void set_blocked_tile_override(int tile);
-void set_blocked_tma(int enabled);
+void set_blocked_tma(int mode);
+void set_blocked_cluster(int c);
 void set_blocked_grid_cap(int cap);
 void set_resident_warps(int w);
 void set_resident_r1_max_warps(int w);

@@ -62,10 +62,11 @@ def test_solve_level_bit_exact_vs_oracle(rtdd, rows, cols, variant, T):
             "level %d: max |diff| %g on %d px" % (level, np.abs(got - want).max(), (got != want).sum())
 
 
-@pytest.mark.parametrize("tile,tma", [(64, 1), (64, 0), (32, 0), (34, 0)])
+@pytest.mark.parametrize("tile,tma,cluster", [(64, 2, 1), (64, 2, 2), (64, 2, 4), (64, 2, 8), (64, 1, 2), (64, 0, 2), (32, 0, 2), (34, 0, 2)])
 @pytest.mark.parametrize("rows,cols", [(1, 1), (64, 128), (65, 129), (67, 120), (203, 317), (270, 480), (300, 700)])
-def test_blocked_kernel_forms_agree(rtdd, rows, cols, tile, tma):
-    """128x64 regions through TMA (persistent) and through LDG, and 128x32 regions: all bit-identical to the oracle."""
+def test_blocked_kernel_forms_agree(rtdd, rows, cols, tile, tma, cluster):
+    """128x64 regions through TMA (persistent clusters sharing edge rows over DSMEM, persistent single CTAs) and through LDG,
+    and 128x32 regions: all bit-identical to the oracle."""
     iters = 29
     for T in (3, 8, 13):
         gray, depth, scribble = random_level(rows, cols, 7 + rows + T)
@@ -73,6 +74,7 @@ def test_blocked_kernel_forms_agree(rtdd, rows, cols, tile, tma):
         ctx = rtdd.DepthDiffusion(rows * 2, cols * 2, 3)
         ctx.set_tuning("blocked_tile", tile)
         ctx.set_tuning("blocked_tma", tma)
+        ctx.set_tuning("blocked_cluster", cluster)
         ctx.set_sweep_variant(2, T)
         d, s, g = to_dev(depth), to_dev(scribble), to_dev(gray)
         try:
@@ -81,7 +83,8 @@ def test_blocked_kernel_forms_agree(rtdd, rows, cols, tile, tma):
             got = to_host(d)
         finally:
             ctx.set_tuning("blocked_tile", 0)
-            ctx.set_tuning("blocked_tma", 1)
+            ctx.set_tuning("blocked_tma", 2)
+            ctx.set_tuning("blocked_cluster", 2)
             ctx.close()
         assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (T, np.abs(got - want).max())
 

@@ -40,11 +40,12 @@ def bits_equal(a, b):
 
 # ---- the persistent kernel's region loop, many trips per CTA, against the oracle ----------------------------------------
 
-@pytest.mark.parametrize("cap", [1, 3, 4])
+@pytest.mark.parametrize("cap,mode,cluster", [(1, 1, 1), (3, 1, 1), (4, 1, 1), (1, 2, 1), (1, 2, 2), (3, 2, 2), (2, 2, 4), (1, 2, 8)])
 @pytest.mark.parametrize("rows,cols", [(203, 317), (270, 480), (300, 700), (540, 960)])
-def test_persistent_region_loop_many_trips_vs_oracle(rtdd, rows, cols, cap):
-    """blocked_grid_cap limits the persistent TMA kernel to `cap` CTAs, so every CTA walks up to dozens of regions: mbarrier
-    phase flips, the next region's TMA loads issued under the current region's sweeps, reuse of the edge tables."""
+def test_persistent_region_loop_many_trips_vs_oracle(rtdd, rows, cols, cap, mode, cluster):
+    """blocked_grid_cap limits the persistent TMA kernels to `cap` CTAs (mode 1) / clusters (mode 2), so every one walks up to
+    dozens of regions: mbarrier phase flips, the next region's TMA loads issued under the current region's sweeps, reuse of
+    the edge tables and -- cluster form -- halo slots and their mbarriers alternating across regions."""
     from tests.test_gpu_parity import random_level
     iters = 29
     for T in (3, 8, 13):
@@ -52,7 +53,8 @@ def test_persistent_region_loop_many_trips_vs_oracle(rtdd, rows, cols, cap):
         want = ob.solve_level(depth, scribble, gray, iters, 1, 2)
         ctx = rtdd.DepthDiffusion(rows * 2, cols * 2, 3)
         ctx.set_tuning("blocked_tile", 64)
-        ctx.set_tuning("blocked_tma", 1)
+        ctx.set_tuning("blocked_tma", mode)
+        ctx.set_tuning("blocked_cluster", cluster)
         ctx.set_tuning("blocked_grid_cap", cap)
         ctx.set_sweep_variant(2, T)
         d, s, g = to_dev(depth), to_dev(scribble), to_dev(gray)
@@ -63,6 +65,8 @@ def test_persistent_region_loop_many_trips_vs_oracle(rtdd, rows, cols, cap):
             res = ctx.level_residual(1)
         finally:
             ctx.set_tuning("blocked_tile", 0)
+            ctx.set_tuning("blocked_tma", 2)
+            ctx.set_tuning("blocked_cluster", 2)
             ctx.set_tuning("blocked_grid_cap", 0)
             ctx.close()
         assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (T, np.abs(got - want).max())

@@ -28,7 +28,7 @@ for variant, T, tile, tma in ((1, 0, 0, 1), (2, 5, 64, 1), (2, 8, 64, 0), (2, 7,
     ctx.sync()
     print(variant, T, tile, tma, float(out.mean()), ctx.level_residual(0))
     ctx.set_tuning("blocked_tile", 0)
-    ctx.set_tuning("blocked_tma", 1)
+    ctx.set_tuning("blocked_tma", 2)
     ctx.close()
 ctx = rtdd.DepthDiffusion(rows, cols)
 o, g, d = to_dev(bgr, 3), to_dev(np.ascontiguousarray(bgr[..., 1])), to_dev(np.full((rows, cols), 120.0, np.float32))
