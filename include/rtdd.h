@@ -123,8 +123,9 @@ int rtdd_selftest_division(rtdd_ctx *ctx, unsigned long long n, unsigned long lo
 int rtdd_set_sweep_variant(rtdd_ctx *ctx, int variant, int sweepsPerPass);
 /* Process-wide tuning knobs for experiments (tools/tune_blocked.py); results never change, only speed.
  * "blocked_tile": 0 auto, 64 = 128x64-pixel regions, 34 = 128x32 regions with 2 rows per warp, 32 = 128x32 with 4 rows per warp;
- * "blocked_tma": 2 (default) TMA-fed persistent thread-block clusters (vertically adjacent CTAs share their edge rows over
- *                distributed shared memory), 1 = TMA-fed persistent single CTAs, 0 = plain LDG form;
+ * "blocked_tma": 3 = TMA-fed persistent thread-block clusters (vertically adjacent CTAs share their edge rows over distributed
+ *                shared memory), 1 = TMA-fed persistent single CTAs, 2 (default) = clusters for levels >= 2^22 pixels and
+ *                single CTAs below (measured), 0 = plain LDG form;
  * "blocked_cluster": CTAs per cluster of the default form (1, 2 (default), 4, 8);
  * "blocked_grid_cap": > 0 limits the persistent form to that many CTAs (tests: every CTA then walks several regions even on
  *                     small levels, so the region loop -- phase flips, re-issue under the sweeps -- is checked against the oracle);
@@ -184,6 +185,12 @@ int rtdd_strip_pull(rtdd_ctx *ctx, int level);
 /* on = 0: the following passes of `level` keep their boundary rows to themselves (the finest level's last pass: nobody
  * reads the ghost rows afterwards); the flags are still raised.  Reset to on by rtdd_strip_neighbours. */
 int rtdd_strip_push_enable(rtdd_ctx *ctx, int level, int on);
+/* The level's LAST pass writing straight into the caller's pitched depth plane and, if depthU8 is non-null, the 8-bit map
+ * (GpuMat::convertTo, ref: src/main.cpp:290): rtdd_strip_pass + rtdd_strip_finish in one where no halo exchange follows (the
+ * finest level).  depth / depthU8 are the FULL planes (row 0 = row 0 of the level, 16-byte aligned rows); every row of the
+ * window is written, ghost rows with their stale values. */
+int rtdd_strip_pass_to(rtdd_ctx *ctx, int level, int firstSweep, int nsweeps, int haloT, float *depth, size_t depthPitch,
+                       uint8_t *depthU8, size_t depthU8Pitch);
 /* cv::pyrUp restricted to destination rows [rowBegin, rowEnd); src and dst are the full planes */
 int rtdd_pyrup_depth_rows(rtdd_ctx *ctx, const float *src, size_t srcPitch, int srcRows, int srcCols,
                           float *dst, size_t dstPitch, int dstRows, int dstCols, int rowBegin, int rowEnd);
@@ -225,6 +232,14 @@ int rtdd_effects_fused(rtdd_ctx *ctx, const uint8_t *orig, size_t origPitch, con
                        const float *depth, size_t depthPitch,
                        uint8_t *desat, size_t desatPitch, uint8_t *haze, size_t hazePitch,
                        uint8_t *defocus, size_t defocusPitch, int rows, int cols);
+
+/* DepthEffect on rows [rowBegin, rowEnd) only (row strips across GPUs): every plane is the FULL image
+ * plane, any of the three outputs may be NULL, and only the strip's rows of the outputs are written -- with exactly the bytes
+ * the whole-image calls put there (defocus: K from the full image's diagonal, ref: src/GPUDepthEffect.cu:42; its summed-area
+ * table is built over the strip plus half a box on each open side). */
+int rtdd_effects_rows(rtdd_ctx *ctx, const uint8_t *orig, size_t origPitch, const uint8_t *gray, size_t grayPitch,
+                      const float *depth, size_t depthPitch, uint8_t *desat, size_t desatPitch, uint8_t *haze, size_t hazePitch,
+                      uint8_t *defocus, size_t defocusPitch, int rows, int cols, int rowBegin, int rowEnd);
 
 /* ---- pyramid ops either side of the path ------------------- */
 
@@ -284,6 +299,46 @@ int rtdd_frame_plane(rtdd_ctx *ctx, int which, int level, void **ptr, size_t *pi
 #define RTDD_PLANE_EDITED   3   /* u8 x 3 */
 #define RTDD_PLANE_BGR      4   /* u8 x 3, level 0 only */
 #define RTDD_PLANE_DEPTH_U8 5   /* u8, level 0 only */
+
+/* rtdd_frame_set_image for a BGR image that already lives on the device (pitched, rows x 3*cols bytes). */
+int rtdd_frame_set_image_device(rtdd_ctx *ctx, const uint8_t *bgrDevice, size_t bgrPitch);
+
+/* ---- one frame of ONE image across several GPUs, row strips (BASELINE configs[4]); no reference counterpart ---------------
+ * The frame loop is main.cpp's (ref: src/main.cpp:232-295).  Every rank = one context on one GPU holding the whole image and
+ * annotation planes (rtdd_frame_set_image*, rtdd_frame_plane); levels of at least minStripPixels pixels are cut into row
+ * strips (rtdd_plan_strips), the coarser ones are solved by every rank.  Halo rows (`halo` per open side, passes of
+ * `passSweeps` sweeps between two exchanges) travel through peer memory (rtdd_strip_set_peers with the neighbours' arenas:
+ * rtdd_arena inside one process after cudaDeviceEnablePeerAccess, rtdd_ipc_export / _import between processes).  All ranks
+ * must issue the same calls.  Owned rows are bit-identical to the one-GPU frame. */
+int rtdd_strip_frame_setup(rtdd_ctx *ctx, int rank, int nranks, int halo, int passSweeps, long long minStripPixels);
+int rtdd_strip_frame_solve(rtdd_ctx *ctx, int maxIterations);
+/* only the finest level, `sweeps` sweeps from the guess its depth plane holds */
+int rtdd_strip_frame_level0(rtdd_ctx *ctx, int sweeps);
+/* this rank's rows of `level`: *split = 0 if the level is solved whole by every rank; own rows [ownBegin, ownEnd), window incl. ghosts */
+int rtdd_strip_frame_rows(rtdd_ctx *ctx, int level, int *split, int *ownBegin, int *ownEnd, int *winBegin, int *winEnd);
+/* ref: src/main.cpp:190-230 on this rank's rows of the finest level; outputs are FULL device planes, only owned rows are written */
+int rtdd_strip_frame_effects(rtdd_ctx *ctx, uint8_t *desat, size_t desatPitch, uint8_t *haze, size_t hazePitch, uint8_t *defocus, size_t defocusPitch);
+
+/* ---- several GPUs from ONE process: one host thread per GPU inside the library (what a C++ host like main.cpp links) -------
+ * rtdd_mgpu_create makes one context per listed device, enables peer access between neighbours and wires their arenas.
+ * halo / passSweeps / minStripPixels <= 0 select the defaults (16 / 8 / 2^22).  Every call below runs on all GPUs concurrently
+ * and returns when all have finished; *msDevice (may be NULL) = the slowest rank's device time. */
+typedef struct rtdd_mgpu rtdd_mgpu;
+int rtdd_mgpu_create(const int *devices, int ndevices, int rows, int cols, int levels, float beta, int halo, int passSweeps,
+                     long long minStripPixels, rtdd_mgpu **out);
+int rtdd_mgpu_destroy(rtdd_mgpu *m);
+int rtdd_mgpu_devices(const rtdd_mgpu *m);
+const char *rtdd_mgpu_last_error(const rtdd_mgpu *m);
+rtdd_ctx *rtdd_mgpu_context(rtdd_mgpu *m, int rank);
+/* configs[4]: the image (HOST, BGR) goes to every GPU; a frame = annotation plane in (HOST, 32 = not annotated), 8-bit map out */
+int rtdd_mgpu_set_image(rtdd_mgpu *m, const uint8_t *bgrHost, size_t bgrPitch);
+int rtdd_mgpu_frame_solve_host_annotation(rtdd_mgpu *m, const uint8_t *annotationHost, size_t annotationPitch, int maxIterations,
+                                          uint8_t *depthU8Host, size_t depthU8Pitch, float *msDevice);
+int rtdd_mgpu_frame_solve(rtdd_mgpu *m, int maxIterations, float *msDevice);      /* annotations already on the devices */
+int rtdd_mgpu_level0(rtdd_mgpu *m, int sweeps, float *msDevice);
+/* configs[3]: nimages independent images, image i on GPU i mod N, every image a full job from HOST buffers */
+int rtdd_mgpu_batch_solve(rtdd_mgpu *m, int nimages, const uint8_t *const *bgrHost, size_t bgrPitch, const uint8_t *const *annotationHost,
+                          size_t annotationPitch, int maxIterations, uint8_t *const *depthU8Host, size_t depthU8Pitch, float *msDevice);
 
 #ifdef __cplusplus
 }

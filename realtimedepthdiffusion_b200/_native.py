@@ -76,6 +76,24 @@ SIGNATURES = {
     "rtdd_frame_paint": (i32, [vp, i32, i32, i32, i32]),
     "rtdd_frame_plane": (i32, [vp, i32, i32, C.POINTER(vp), C.POINTER(sz), C.POINTER(i32), C.POINTER(i32)]),
     "rtdd_frame_effects": (i32, [vp, vp, sz, vp, sz, vp, sz]),
+    "rtdd_frame_set_image_device": (i32, [vp, vp, sz]),
+    "rtdd_strip_pass_to": (i32, [vp, i32, i32, i32, i32, vp, sz, vp, sz]),
+    "rtdd_effects_rows": (i32, [vp, vp, sz, vp, sz, vp, sz, vp, sz, vp, sz, vp, sz, i32, i32, i32, i32]),
+    "rtdd_strip_frame_setup": (i32, [vp, i32, i32, i32, i32, C.c_longlong]),
+    "rtdd_strip_frame_solve": (i32, [vp, i32]),
+    "rtdd_strip_frame_level0": (i32, [vp, i32]),
+    "rtdd_strip_frame_rows": (i32, [vp, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]),
+    "rtdd_strip_frame_effects": (i32, [vp, vp, sz, vp, sz, vp, sz]),
+    "rtdd_mgpu_create": (i32, [vp, i32, i32, i32, i32, f32, i32, i32, C.c_longlong, C.POINTER(vp)]),
+    "rtdd_mgpu_destroy": (i32, [vp]),
+    "rtdd_mgpu_devices": (i32, [vp]),
+    "rtdd_mgpu_last_error": (C.c_char_p, [vp]),
+    "rtdd_mgpu_context": (vp, [vp, i32]),
+    "rtdd_mgpu_set_image": (i32, [vp, vp, sz]),
+    "rtdd_mgpu_frame_solve_host_annotation": (i32, [vp, vp, sz, i32, vp, sz, C.POINTER(f32)]),
+    "rtdd_mgpu_frame_solve": (i32, [vp, i32, C.POINTER(f32)]),
+    "rtdd_mgpu_level0": (i32, [vp, i32, C.POINTER(f32)]),
+    "rtdd_mgpu_batch_solve": (i32, [vp, i32, vp, sz, vp, sz, i32, vp, sz, C.POINTER(f32)]),
 }
 
 from .refnames import SHIM_SIGNATURES, SHIM_SYMBOLS, bind_reference_api  # noqa: E402,F401

@@ -172,11 +172,13 @@ effects_kernel(const uint8_t *__restrict__ orig, size_t origPitch, const uint8_t
                const float *__restrict__ depth, size_t depthPitch,
                uint8_t *__restrict__ desat, size_t desatPitch, uint8_t *__restrict__ haze, size_t hazePitch,
                uint8_t *__restrict__ defocus, size_t defocusPitch,
-               const uint4 *__restrict__ sat, const uint4 *__restrict__ aux, int K, int rows, int cols)
+               const uint4 *__restrict__ sat, const uint4 *__restrict__ aux, int K, int rows, int cols, int yBegin, int yEnd, int satRow0, int satRows)
 {
+    // Rows [yBegin, yEnd) of the image are produced (the whole image: 0, rows; a row strip of one GPU: rtdd_effects_rows).  The
+    // summed-area table covers image rows [satRow0, satRow0 + satRows); a box that leaves it takes the raster path below.
     const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    const int y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x4 >= cols || y >= rows) return;
+    const int y = yBegin + blockIdx.y * blockDim.y + threadIdx.y;
+    if (x4 >= cols || y >= yEnd) return;
     const int n = min(4, cols - x4);
 
     unsigned int c[4][3];
@@ -244,15 +246,15 @@ effects_kernel(const uint8_t *__restrict__ orig, size_t origPitch, const uint8_t
                 // (h > 0 guarantees a non-empty clipped window for an in-image pixel)
                 const int count = (x1 - x0) * (y1 - y0);
                 float sb, sg, sr;
-                if (count <= 65793) {      // count * 255 < 2^24: the reference's fp32 sums are exact integers
-                    const uint4 s11 = sat_at(sat, aux, satPitch, y1, x1);
-                    const uint4 s01 = sat_at(sat, aux, satPitch, y0, x1);
-                    const uint4 s10 = sat_at(sat, aux, satPitch, y1, x0);
-                    const uint4 s00 = sat_at(sat, aux, satPitch, y0, x0);
+                if (count <= 65793 && y0 >= satRow0 && y1 <= satRow0 + satRows) {      // count * 255 < 2^24: the reference's fp32 sums are exact integers
+                    const uint4 s11 = sat_at(sat, aux, satPitch, y1 - satRow0, x1);
+                    const uint4 s01 = sat_at(sat, aux, satPitch, y0 - satRow0, x1);
+                    const uint4 s10 = sat_at(sat, aux, satPitch, y1 - satRow0, x0);
+                    const uint4 s00 = sat_at(sat, aux, satPitch, y0 - satRow0, x0);
                     sb = (float)(s11.x - s01.x - s10.x + s00.x);
                     sg = (float)(s11.y - s01.y - s10.y + s00.y);
                     sr = (float)(s11.z - s01.z - s10.z + s00.z);
-                } else {                   // huge window: replay the reference's raster-order fp32 accumulation
+                } else {                   // huge window (or one beyond a strip's table): replay the reference's raster-order fp32 accumulation
                     sb = 0.0f; sg = 0.0f; sr = 0.0f;
                     for (int py = y0; py < y1; py++) {
                         const uint8_t *r = orig + (size_t)py * origPitch;
@@ -280,20 +282,24 @@ template <bool DESAT, bool HAZE, bool DEFOCUS>
 static cudaError_t launch_effects(cudaStream_t s, const uint8_t *orig, size_t origPitch, const uint8_t *gray, size_t grayPitch,
                                   const float *depth, size_t depthPitch, uint8_t *desat, size_t desatPitch,
                                   uint8_t *haze, size_t hazePitch, uint8_t *defocus, size_t defocusPitch,
-                                  const uint4 *sat, const uint4 *aux, int K, int rows, int cols)
+                                  const uint4 *sat, const uint4 *aux, int K, int rows, int cols, int yBegin = 0, int yEnd = -1,
+                                  int satRow0 = 0, int satRows = -1)
 {
+    if (yEnd < 0) yEnd = rows;
+    if (satRows < 0) satRows = rows;
     bool al = aligned4(orig, origPitch) && aligned16(depth, depthPitch);
     if (DESAT) al = al && aligned4(gray, grayPitch) && aligned4(desat, desatPitch);
     if (HAZE) al = al && aligned4(haze, hazePitch);
     if (DEFOCUS) al = al && aligned4(defocus, defocusPitch);
     dim3 block(32, 8);
-    dim3 grid(rtdd_div_up(rtdd_div_up(cols, 4), block.x), rtdd_div_up(rows, block.y));
+    if (yEnd <= yBegin) return cudaSuccess;
+    dim3 grid(rtdd_div_up(rtdd_div_up(cols, 4), block.x), rtdd_div_up(yEnd - yBegin, block.y));
     if (al)
         effects_kernel<true, DESAT, HAZE, DEFOCUS><<<grid, block, 0, s>>>(orig, origPitch, gray, grayPitch, depth, depthPitch,
-            desat, desatPitch, haze, hazePitch, defocus, defocusPitch, sat, aux, K, rows, cols);
+            desat, desatPitch, haze, hazePitch, defocus, defocusPitch, sat, aux, K, rows, cols, yBegin, yEnd, satRow0, satRows);
     else
         effects_kernel<false, DESAT, HAZE, DEFOCUS><<<grid, block, 0, s>>>(orig, origPitch, gray, grayPitch, depth, depthPitch,
-            desat, desatPitch, haze, hazePitch, defocus, defocusPitch, sat, aux, K, rows, cols);
+            desat, desatPitch, haze, hazePitch, defocus, defocusPitch, sat, aux, K, rows, cols, yBegin, yEnd, satRow0, satRows);
     return cudaGetLastError();
 }
 
@@ -343,23 +349,26 @@ cudaError_t launch_sat_build(cudaStream_t s, void *scratch, const uint8_t *orig,
 cudaError_t launch_defocus(cudaStream_t s, void *scratch, const uint8_t *orig, size_t origPitch, const uint8_t *gray, size_t grayPitch,
                            const float *depth, size_t depthPitch, uint8_t *defocus, size_t defocusPitch,
                            uint8_t *desat, size_t desatPitch, uint8_t *haze, size_t hazePitch,
-                           int rows, int cols, int *launched, bool buildSat)
+                           int rows, int cols, int *launched, bool buildSat, int yBegin, int yEnd, int satRow0, int satRows)
 {
+    // all planes are the FULL image planes; the summed-area table covers image rows [satRow0, satRow0 + satRows)
+    if (yEnd < 0) yEnd = rows;
+    if (satRows < 0) { satRow0 = 0; satRows = rows; }
     uint4 *sat = (uint4 *)scratch;
-    uint4 *aux = sat + (size_t)(rows + 1) * (cols + 1);
+    uint4 *aux = sat + (size_t)(satRows + 1) * (cols + 1);
     const int K = defocus_kernel_size(rows, cols);
     *launched = 0;
     if (buildSat) {
-        cudaError_t e = launch_sat_build(s, scratch, orig, origPitch, rows, cols);
+        cudaError_t e = launch_sat_build(s, scratch, orig + (size_t)satRow0 * origPitch, origPitch, satRows, cols);
         if (e != cudaSuccess) return e;
         *launched = 3;
     }
     *launched += 1;
     if (desat && haze)
         return launch_effects<true, true, true>(s, orig, origPitch, gray, grayPitch, depth, depthPitch, desat, desatPitch,
-                                                haze, hazePitch, defocus, defocusPitch, sat, aux, K, rows, cols);
+                                                haze, hazePitch, defocus, defocusPitch, sat, aux, K, rows, cols, yBegin, yEnd, satRow0, satRows);
     return launch_effects<false, false, true>(s, orig, origPitch, nullptr, 0, depth, depthPitch, nullptr, 0, nullptr, 0,
-                                              defocus, defocusPitch, sat, aux, K, rows, cols);
+                                              defocus, defocusPitch, sat, aux, K, rows, cols, yBegin, yEnd, satRow0, satRows);
 }
 
 }  // namespace rtdd

@@ -588,7 +588,7 @@ int rtdd_set_tuning(rtdd_ctx *ctx, const char *key, int value)
         destroy_graphs(ctx);
         return 0;
     }
-    if (strcmp(key, "blocked_tma") == 0 && value >= 0 && value <= 2) {
+    if (strcmp(key, "blocked_tma") == 0 && value >= 0 && value <= 3) {
         rtdd::set_blocked_tma(value);
         DeviceGuard guard(ctx->device);
         cudaStreamSynchronize(ctx->stream);
@@ -924,7 +924,24 @@ int rtdd_strip_wait(rtdd_ctx *ctx, int level)
     return 0;
 }
 
+static int strip_pass_impl(rtdd_ctx *ctx, int level, int firstSweep, int nsweeps, int haloT, float *depth, size_t depthPitch, uint8_t *u8, size_t u8Pitch);
+
 int rtdd_strip_pass(rtdd_ctx *ctx, int level, int firstSweep, int nsweeps, int haloT)
+{
+    return strip_pass_impl(ctx, level, firstSweep, nsweeps, haloT, nullptr, 0, nullptr, 0);
+}
+
+// The level's LAST pass writing straight into the caller's pitched depth plane (and, optionally, the 8-bit map): replaces
+// rtdd_strip_pass + rtdd_strip_finish where no halo exchange follows (the finest level).  depth / depthU8 are the FULL planes
+// (row 0 of the level); every row of the window is written, the ghost rows with their stale values (they belong to other ranks).
+int rtdd_strip_pass_to(rtdd_ctx *ctx, int level, int firstSweep, int nsweeps, int haloT, float *depth, size_t depthPitch, uint8_t *depthU8, size_t depthU8Pitch)
+{
+    if (!ctx) return RTDD_E_ARG;
+    if (!depth || !target_ok(depth, depthPitch)) return rtdd_fail(ctx, RTDD_E_ARG, "rtdd_strip_pass_to (depth plane must be 16-byte aligned)");
+    return strip_pass_impl(ctx, level, firstSweep, nsweeps, haloT, depth, depthPitch, depthU8, depthU8Pitch);
+}
+
+static int strip_pass_impl(rtdd_ctx *ctx, int level, int firstSweep, int nsweeps, int haloT, float *depth, size_t depthPitch, uint8_t *u8, size_t u8Pitch)
 {
     if (!ctx) return RTDD_E_ARG;
     if (level < 0 || level >= ctx->levels) return rtdd_fail(ctx, RTDD_E_ARG, "rtdd_strip_pass");
@@ -944,7 +961,12 @@ int rtdd_strip_pass(rtdd_ctx *ctx, int level, int firstSweep, int nsweeps, int h
     // default: measured on the 16K level-0 pass, accumulating it costs 4.14 vs 3.87 ms per pass (ncu launch lists,
     // profiles/r01_strip_path_vs_level_graph.txt)
     const bool wantResidual = ctx->stripResidual;
-    const rtdd::SweepTarget tgt = {nullptr, 0, nullptr, 0, wantResidual ? L.dResidual : nullptr};
+    rtdd::SweepTarget tgt = {nullptr, 0, nullptr, 0, wantResidual ? L.dResidual : nullptr};
+    if (depth) {
+        tgt.x = (float *)((char *)depth + (size_t)L.stripBegin * depthPitch);
+        tgt.pitchX = (int)(depthPitch / sizeof(float));
+        if (u8) { tgt.u8 = u8 + (size_t)L.stripBegin * u8Pitch; tgt.pitchU8 = (int)u8Pitch; }
+    }
     if (wantResidual) RTDD_TRY(cudaMemsetAsync(L.dResidual, 0, sizeof(unsigned int), ctx->stream), "rtdd_strip_pass");
     rtdd::HaloPush hp = {};
     bool fused = L.stripFused && (ctx->peerUp || ctx->peerDn);
@@ -995,7 +1017,7 @@ int rtdd_strip_pass(rtdd_ctx *ctx, int level, int firstSweep, int nsweeps, int h
         hp.waitValue = (L.stripPassAbs > L.stripFirstPassAbs) ? L.stripPassAbs : 0;   // first pass of a level: nothing to wait for
     }
     RTDD_TRY(rtdd::launch_sweep_blocked(ctx->stream, W, ctx->dLut, L.x[src], L.x[src + 1], L.x[dst], L.x[dst + 1], pack, haloT, nsweeps, 0.99f,
-                                        firstSweep == 0, ctx->smCount, &tgt, fused ? &hp : nullptr), "rtdd_strip_pass");
+                                        firstSweep == 0, ctx->smCount, (tgt.x || tgt.res) ? &tgt : nullptr, fused ? &hp : nullptr), "rtdd_strip_pass");
     if (fused) { L.stripCtaAbs = hp.doneTarget; L.stripPassAbs++; }
     ctx->launches++;
     L.stripPair = dst;
@@ -1174,6 +1196,51 @@ int rtdd_effects_fused(rtdd_ctx *ctx, const uint8_t *orig, size_t origPitch, con
     return 0;
 }
 
+// DepthEffect on a row strip: rows [rowBegin, rowEnd) of the outputs, identical to what the whole-image calls
+// put there.  Desaturation and haze are per pixel; defocus reads image rows up to half a box beyond the strip, so its summed-area
+// table is built over the strip plus K/2 + 8 rows on each open side (K from the FULL image's diagonal, ref: src/GPUDepthEffect.cu:42;
+// a depth beyond 255 can ask for more -- such a box takes the reference's raster path on the full image, still exact).
+int rtdd_effects_rows(rtdd_ctx *ctx, const uint8_t *orig, size_t origPitch, const uint8_t *gray, size_t grayPitch,
+                      const float *depth, size_t depthPitch, uint8_t *desat, size_t desatPitch, uint8_t *haze, size_t hazePitch,
+                      uint8_t *defocus, size_t defocusPitch, int rows, int cols, int rowBegin, int rowEnd)
+{
+    if (!ctx) return RTDD_E_ARG;
+    if (!orig || !depth || (desat && !gray) || rows < 0 || cols < 0 || rowBegin < 0 || rowEnd > rows || rowEnd < rowBegin)
+        return rtdd_fail(ctx, RTDD_E_ARG, "rtdd_effects_rows");
+    if (rowEnd == rowBegin || cols == 0) return 0;
+    DeviceGuard guard(ctx->device);
+    cudaStream_t s = ctx->stream;
+    const size_t o3 = (size_t)rowBegin, n = (size_t)(rowEnd - rowBegin);
+    if (defocus) {
+        const int K = rtdd::defocus_kernel_size(rows, cols);
+        const int reach = K / 2 + 8;
+        const int v0 = rowBegin - reach > 0 ? rowBegin - reach : 0;
+        const int v1 = rowEnd + reach < rows ? rowEnd + reach : rows;
+        int rc = ensure_sat(ctx, v1 - v0, cols);
+        if (rc) return rc;
+        ctx->frameSatValid = false;
+        const bool all = desat && haze;
+        int launched = 0;
+        RTDD_TRY(rtdd::launch_defocus(s, ctx->satScratch, orig, origPitch, all ? gray : nullptr, grayPitch, depth, depthPitch, defocus, defocusPitch,
+                                      all ? desat : nullptr, desatPitch, all ? haze : nullptr, hazePitch, rows, cols, &launched, true,
+                                      rowBegin, rowEnd, v0, v1 - v0), "rtdd_effects_rows (defocus)");
+        ctx->launches += launched;
+        if (all) return 0;
+    }
+    if (desat) {
+        RTDD_TRY(rtdd::launch_desaturate(s, orig + o3 * origPitch, origPitch, gray + o3 * grayPitch, grayPitch,
+                                         (const float *)((const char *)depth + o3 * depthPitch), depthPitch, desat + o3 * desatPitch, desatPitch, (int)n, cols),
+                 "rtdd_effects_rows (desaturation)");
+        ctx->launches++;
+    }
+    if (haze) {
+        RTDD_TRY(rtdd::launch_haze(s, orig + o3 * origPitch, origPitch, (const float *)((const char *)depth + o3 * depthPitch), depthPitch,
+                                   haze + o3 * hazePitch, hazePitch, (int)n, cols), "rtdd_effects_rows (haze)");
+        ctx->launches++;
+    }
+    return 0;
+}
+
 // ---- pyramid ops -----------------------------------------------------------------
 
 int rtdd_bgr2gray(rtdd_ctx *ctx, const uint8_t *bgr, size_t bgrPitch, uint8_t *gray, size_t grayPitch, int rows, int cols)
@@ -1281,6 +1348,36 @@ int rtdd_frame_set_image(rtdd_ctx *ctx, const uint8_t *bgrHost, size_t bgrPitch)
     for (int l = 1; l < ctx->levels; l++) {
         RtddFrameLevel &P = ctx->fl[l - 1], &F = ctx->fl[l];
         RTDD_TRY(rtdd::launch_pyrdown_gray(s, P.gray, P.grayPitch, P.grayRows, P.grayCols, F.gray, F.grayPitch), "rtdd_frame_set_image");
+        ctx->launches++;
+    }
+    ctx->imageSet = true;
+    ctx->frameSatValid = false;
+    return 0;
+}
+
+// rtdd_frame_set_image for an image that is already on the device (strip benches synthesise the 16K image there)
+int rtdd_frame_set_image_device(rtdd_ctx *ctx, const uint8_t *bgrDevice, size_t bgrPitch)
+{
+    if (!ctx) return RTDD_E_ARG;
+    if (!bgrDevice || bgrPitch < (size_t)ctx->cols * 3) return rtdd_fail(ctx, RTDD_E_ARG, "rtdd_frame_set_image_device");
+    DeviceGuard guard(ctx->device);
+    int rc = frame_alloc(ctx);
+    if (rc) return rc;
+    cudaStream_t s = ctx->stream;
+    RTDD_TRY(cudaMemcpy2DAsync(ctx->bgr, ctx->bgrPitch, bgrDevice, bgrPitch, (size_t)ctx->cols * 3, ctx->rows, cudaMemcpyDeviceToDevice, s),
+             "rtdd_frame_set_image_device (copy)");
+    for (int l = 0; l < ctx->levels; l++) {
+        RtddFrameLevel &F = ctx->fl[l];
+        RTDD_TRY(cudaMemsetAsync(F.scribble, 0, F.scribblePitch * F.rows, s), "rtdd_frame_set_image_device");
+        RTDD_TRY(cudaMemsetAsync(F.edited, 0, F.editedPitch * F.rows, s), "rtdd_frame_set_image_device");
+        RTDD_TRY(rtdd::launch_fill_f32(s, F.depth, F.depthPitch, F.rows, F.cols, 255.0f), "rtdd_frame_set_image_device");
+        ctx->launches++;
+    }
+    RTDD_TRY(rtdd::launch_bgr2gray(s, ctx->bgr, ctx->bgrPitch, ctx->fl[0].gray, ctx->fl[0].grayPitch, ctx->rows, ctx->cols), "rtdd_frame_set_image_device");
+    ctx->launches++;
+    for (int l = 1; l < ctx->levels; l++) {
+        RtddFrameLevel &P = ctx->fl[l - 1], &F = ctx->fl[l];
+        RTDD_TRY(rtdd::launch_pyrdown_gray(s, P.gray, P.grayPitch, P.grayRows, P.grayCols, F.gray, F.grayPitch), "rtdd_frame_set_image_device");
         ctx->launches++;
     }
     ctx->imageSet = true;

@@ -79,6 +79,13 @@ struct RtddGraph {
     std::vector<RtddLevelTiming> timing;   // what rtdd_level_sweep_ms reports after THIS graph ran (copied into the levels at every launch)
 };
 
+// one rank's share of a row-strip frame (rtdd_strip_frame_*): the decomposition of every level, as planned by rtdd_plan_strips
+struct RtddStripFrame {
+    bool ready = false;
+    int rank = 0, nranks = 1, halo = 16, passSweeps = 8;
+    std::vector<int> split, ownBegin, ownEnd;      // per level; own ranges indexed [level * nranks + rank]
+};
+
 struct rtdd_ctx {
     int device = 0;
     int rows = 0, cols = 0, levels = 0;
@@ -113,6 +120,7 @@ struct rtdd_ctx {
     bool imageSet = false;
     bool stripResidual = false;        // rtdd_strip_pass also fills the level's residual word (+7 % per pass at 16K: only rtdd_solve_level_converge asks)
     bool peerStaging = false;          // rtdd_set_tuning("strip_peer_staging", 1): halo rows travel through rtdd_strip_push / _pull
+    RtddStripFrame sf;
     bool frameSatValid = false;        // satScratch holds the summed-area table of the frame image (rtdd_frame_effects)
     // defocus scratch (summed-area tables), grown on demand
     void *satScratch = nullptr; size_t satBytes = 0;
@@ -241,6 +249,7 @@ cudaError_t launch_quantise(cudaStream_t s, const float *src, size_t srcPitch, u
 cudaError_t launch_fill_f32(cudaStream_t s, float *dst, size_t pitch, int rows, int cols, float v);
 
 // effect_kernels.cu
+int defocus_kernel_size(int rows, int cols);
 cudaError_t launch_desaturate(cudaStream_t s, const uint8_t *orig, size_t origPitch, const uint8_t *gray, size_t grayPitch,
                               const float *depth, size_t depthPitch, uint8_t *out, size_t outPitch, int rows, int cols);
 cudaError_t launch_haze(cudaStream_t s, const uint8_t *orig, size_t origPitch, const float *depth, size_t depthPitch,
@@ -252,6 +261,6 @@ cudaError_t launch_sat_build(cudaStream_t s, void *scratch, const uint8_t *orig,
 cudaError_t launch_defocus(cudaStream_t s, void *scratch, const uint8_t *orig, size_t origPitch, const uint8_t *gray, size_t grayPitch,
                            const float *depth, size_t depthPitch, uint8_t *defocus, size_t defocusPitch,
                            uint8_t *desat, size_t desatPitch, uint8_t *haze, size_t hazePitch,
-                           int rows, int cols, int *launched, bool buildSat = true);
+                           int rows, int cols, int *launched, bool buildSat = true, int yBegin = 0, int yEnd = -1, int satRow0 = 0, int satRows = -1);
 
 }  // namespace rtdd

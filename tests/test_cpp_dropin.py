@@ -45,3 +45,38 @@ def test_main_like_same_output_with_reference_kernels_and_with_librtdd(rows, col
         assert r.returncode == 0, r.stdout
         outs[tag] = [ln for ln in r.stdout.splitlines() if ln.startswith("levels")][-1]
     assert outs["rtdd"] == outs["ref"], outs
+
+
+# ---- the multi-GPU entry points from a C++ host ------------------------------------------------------------------------------
+
+def build_mgpu_host():
+    os.makedirs(BUILD, exist_ok=True)
+    out = os.path.join(BUILD, "mgpu_host")
+    libdir = os.path.join(ROOT, "realtimedepthdiffusion_b200", "lib")
+    cmd = ["g++", "-std=c++17", "-O1", os.path.join(ROOT, "tests", "cpp", "mgpu_host.cpp"), "-I", os.path.join(ROOT, "include"),
+           "-I", os.path.join(CUDA, "include"), "-L", libdir, "-lrtdd", "-L", os.path.join(CUDA, "lib64"), "-lcudart", "-Wl,-rpath," + libdir, "-o", out]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
+    return out
+
+
+def test_mgpu_host_links_against_the_c_abi():
+    """tests/cpp/mgpu_host.cpp uses only include/rtdd.h + the CUDA runtime: rtdd_mgpu_* and rtdd_strip_frame_* resolve from librtdd.so."""
+    exe = build_mgpu_host()
+    undefined = subprocess.run(["nm", "-u", exe], stdout=subprocess.PIPE, text=True).stdout
+    for fn in ("rtdd_mgpu_create", "rtdd_mgpu_set_image", "rtdd_mgpu_frame_solve_host_annotation", "rtdd_mgpu_batch_solve", "rtdd_mgpu_destroy",
+               "rtdd_strip_frame_effects", "rtdd_strip_frame_rows"):
+        assert re.search(r"\b%s\b" % fn, undefined), fn
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ngpus,rows,cols,iters", [(2, 1536, 2048, 1000), (2, 1081, 1923, 300)])
+def test_mgpu_host_strips_effects_and_batch_identical_to_one_gpu(ngpus, rows, cols, iters):
+    """One process, one host thread per GPU inside librtdd.so, peer access instead of IPC: strips, effects on strips and the batch
+    must reproduce the single-GPU bytes.  Needs >= 2 GPUs (gpurun --gpus 2); the program itself reports 'skipped' otherwise."""
+    exe = build_mgpu_host()
+    r = subprocess.run([exe, str(ngpus), str(rows), str(cols), str(iters)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=280)
+    assert r.returncode == 0, r.stdout
+    if "skipped" in r.stdout:
+        pytest.skip(r.stdout.strip())
+    assert "all identical" in r.stdout, r.stdout

@@ -62,7 +62,7 @@ def test_solve_level_bit_exact_vs_oracle(rtdd, rows, cols, variant, T):
             "level %d: max |diff| %g on %d px" % (level, np.abs(got - want).max(), (got != want).sum())
 
 
-@pytest.mark.parametrize("tile,tma,cluster", [(64, 2, 1), (64, 2, 2), (64, 2, 4), (64, 2, 8), (64, 1, 2), (64, 0, 2), (32, 0, 2), (34, 0, 2)])
+@pytest.mark.parametrize("tile,tma,cluster", [(64, 3, 1), (64, 3, 2), (64, 3, 4), (64, 3, 8), (64, 1, 2), (64, 0, 2), (32, 0, 2), (34, 0, 2)])
 @pytest.mark.parametrize("rows,cols", [(1, 1), (64, 128), (65, 129), (67, 120), (203, 317), (270, 480), (300, 700)])
 def test_blocked_kernel_forms_agree(rtdd, rows, cols, tile, tma, cluster):
     """128x64 regions through TMA (persistent clusters sharing edge rows over DSMEM, persistent single CTAs) and through LDG,

@@ -40,7 +40,7 @@ def bits_equal(a, b):
 
 # ---- the persistent kernel's region loop, many trips per CTA, against the oracle ----------------------------------------
 
-@pytest.mark.parametrize("cap,mode,cluster", [(1, 1, 1), (3, 1, 1), (4, 1, 1), (1, 2, 1), (1, 2, 2), (3, 2, 2), (2, 2, 4), (1, 2, 8)])
+@pytest.mark.parametrize("cap,mode,cluster", [(1, 1, 1), (3, 1, 1), (4, 1, 1), (1, 3, 1), (1, 3, 2), (3, 3, 2), (2, 3, 4), (1, 3, 8)])
 @pytest.mark.parametrize("rows,cols", [(203, 317), (270, 480), (300, 700), (540, 960)])
 def test_persistent_region_loop_many_trips_vs_oracle(rtdd, rows, cols, cap, mode, cluster):
     """blocked_grid_cap limits the persistent TMA kernels to `cap` CTAs (mode 1) / clusters (mode 2), so every one walks up to
@@ -228,6 +228,65 @@ def test_16k_finest_level_ab_reference(rtdd, size, sweeps):
     del results
 
 
+# ---- DepthEffect on row strips (one GPU plays every rank in turn) and the huge-box fallback ------------------------------------
+
+@pytest.mark.parametrize("rows,cols,nstrips", [(270, 480, 3), (1080, 1920, 4), (203, 317, 2)])
+def test_effects_on_row_strips_equal_the_whole_image(rtdd, rows, cols, nstrips):
+    from tests.test_gpu_parity import effect_inputs
+    import ctypes as C
+    from realtimedepthdiffusion_b200._native import lib
+    bgr, gray, depth = effect_inputs(rows, cols, 5)
+    depth = depth.copy()
+    depth[::17, ::13] = 300.0                                    # boxes wider than the strip's table reach: raster path, still exact
+    ctx = rtdd.DepthDiffusion(rows, cols)
+    o, g, d = to_dev(bgr, 3), to_dev(gray), to_dev(depth)
+    whole = [to_dev(np.zeros_like(bgr), 3) for _ in range(3)]
+    ctx.effects_fused(o, g, d, *whole)
+    bounds = [(k * rows) // nstrips for k in range(nstrips)] + [rows]
+    for subset in ((1, 1, 1), (0, 0, 1), (1, 0, 0), (0, 1, 1)):
+        strips = [to_dev(np.zeros_like(bgr), 3) for _ in range(3)]
+        for k in range(nstrips):
+            args = []
+            for use, t in zip(subset, strips):
+                args += [C.c_void_p(t.data_ptr()) if use else C.c_void_p(0), t.stride(0)]
+            ctx._ck(lib.rtdd_effects_rows(ctx._h, ptr(o), pitch(o), ptr(g), pitch(g), ptr(d), pitch(d), *args, rows, cols, bounds[k], bounds[k + 1]))
+        ctx.sync()
+        for use, a, b in zip(subset, whole, strips):
+            if use:
+                assert torch.equal(a, b)
+    want = ob.defocus(bgr, depth)
+    assert np.array_equal(to_host(whole[2], 3), want)
+    ctx.close()
+
+
+@need_ref
+def test_defocus_box_beyond_256_takes_the_raster_path_ab_reference(rtdd):
+    """K > 256 needs a diagonal beyond 10 240 pixels (ref: src/GPUDepthEffect.cu:42): 7400 x 7400 -> K = 261.  A box side above 256
+    makes the reference's fp32 sums inexact, so the exact summed-area table is not allowed there and the kernel replays the
+    reference's raster-order accumulation (effect_kernels.cu).  Mostly shallow depths keep the reference's own gather short."""
+    from realtimedepthdiffusion_b200 import _native
+    from realtimedepthdiffusion_b200.api import pitched_empty
+    rows = cols = 7400
+    g = torch.Generator(device="cuda")
+    g.manual_seed(3)
+    bgr = pitched_empty(rows, cols, torch.uint8, "cuda", channels=3)
+    bgr.copy_(torch.randint(0, 256, (rows, cols * 3), generator=g, device="cuda", dtype=torch.uint8))
+    depth = pitched_empty(rows, cols, torch.float32, "cuda")
+    depth.copy_(torch.rand((rows, cols), generator=g, device="cuda") * 12.0)
+    idx = torch.randint(0, rows * cols, (400,), generator=g, device="cuda")
+    depth[idx // cols, idx % cols] = 252.0 + 3.0 * torch.rand(400, generator=g, device="cuda")      # a in 258 .. 261
+    outs = []
+    for api in (ob.ref_api(), _native.shims):
+        out = pitched_empty(rows, cols, torch.uint8, "cuda", channels=3, fill=0)
+        torch.cuda.synchronize()
+        api["GPUSimulateDefocus"](ptr(bgr), pitch(bgr), ptr(depth), pitch(depth), ptr(out), pitch(out), rows, cols)
+        torch.cuda.synchronize()
+        outs.append(out)
+    assert torch.equal(outs[0], outs[1])
+    big = (depth.contiguous() * 261.0 / 255.0).int() > 256
+    assert int(big.sum()) >= 300                                 # the raster path really ran
+
+
 # ---- BASELINE configs[0]: every dataset pair ---------------------------------------------------------------------------
 
 @pytest.mark.skipif(not dataset.have_pack() or not os.path.exists(os.path.join(GOLD, "ref_dataset.json")), reason="dataset goldens missing")
@@ -255,6 +314,24 @@ def test_every_dataset_pair_equals_the_reference(rtdd, name):
 
 
 # ---- row strips on real GPUs (needs >= 2 devices: skipped on the 1-GPU test box, run with gpurun --gpus 2) ----------------
+
+@pytest.mark.skipif(torch.cuda.is_available() and torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("extra", [[], ["--level0-sweeps", "20"], ["--effects"]])
+def test_native_strip_frame_two_processes_bit_identical_to_one_gpu(extra):
+    """The C++ strip frame (rtdd_strip_frame_*), one process per GPU, peers through CUDA IPC: fp32 depth, u8 map and -- with
+    --effects -- the three DepthEffect passes on every rank's rows equal the one-GPU frame bit for bit."""
+    import socket
+    with socket.socket() as so:
+        so.bind(("127.0.0.1", 0))
+        port = so.getsockname()[1]
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(ROOT, "tools", "strips_native.py"), "--size", "2048", "--steps", "2", "--warmup", "1",
+           "--halo", "8", "--min-strip-pixels", "200000", "--check"] + extra
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
+    assert line["bit_identical_to_single_gpu"] is True and any(line["split_levels"])
+
 
 @pytest.mark.skipif(torch.cuda.is_available() and torch.cuda.device_count() < 2, reason="needs 2 GPUs")
 @pytest.mark.parametrize("mode", ["--fused", "--staged", ""])

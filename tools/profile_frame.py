@@ -16,6 +16,10 @@ frames = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 rows, cols, seed = WORKLOADS[name]
 bgr, scribble, edited = synth.synth_case(rows, cols, seed)
 ctx = rtdd.DepthDiffusion(rows, cols)
+if "RTDD_TMA" in os.environ:
+    ctx.set_tuning("blocked_tma", int(os.environ["RTDD_TMA"]))
+if "RTDD_CLUSTER" in os.environ:
+    ctx.set_tuning("blocked_cluster", int(os.environ["RTDD_CLUSTER"]))
 ctx.frame_set_image(bgr)
 out = np.zeros((rows, cols), np.uint8)
 for _ in range(frames):

@@ -17,7 +17,10 @@ for name in which:
     rows, cols, seed = sizes[name]
     bgr, scribble, edited = synth.synth_case(rows, cols, seed)
     ref = None
-    for mode, cl, T in ((1, 1, 0), (2, 1, 0), (2, 2, 0), (2, 4, 0), (2, 2, 6), (2, 2, 7), (2, 2, 10), (2, 4, 11), (2, 2, 16), (2, 4, 16)):
+    combos = ((1, 1, 0), (3, 1, 0), (3, 2, 0), (3, 4, 0), (3, 2, 6), (3, 2, 7), (3, 2, 10), (3, 4, 11), (3, 2, 16), (3, 4, 16), (2, 2, 0))
+    if os.environ.get("RTDD_QUICK"):
+        combos = ((1, 1, 0), (3, 1, 0), (3, 2, 0), (2, 2, 0))
+    for mode, cl, T in combos:
         ctx = rtdd.DepthDiffusion(rows, cols)
         ctx.set_tuning("blocked_tma", mode)
         ctx.set_tuning("blocked_cluster", cl)
