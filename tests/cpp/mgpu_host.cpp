@@ -64,7 +64,8 @@ int main(int argc, char **argv)
     CK(rtdd_load_weights(one, 0.4f));
     CK(rtdd_frame_set_image(one, bgr.data(), (size_t)cols * 3));
     std::vector<uint8_t> want((size_t)rows * cols), got((size_t)rows * cols, 0);
-    CK(rtdd_frame_solve_host_annotation(one, ann.data(), cols, iters, want.data(), cols));
+    // three frames on both sides: like main.cpp, a frame starts from the previous frame's coarsest-level solution (main.cpp:257)
+    for (int rep = 0; rep < 3; rep++) CK(rtdd_frame_solve_host_annotation(one, ann.data(), cols, iters, want.data(), cols));
 
     // ---- 1. row strips over ngpus ----
     rtdd_mgpu *m = nullptr;
