@@ -379,8 +379,77 @@ def run_native(args, dist, rank, world, local):
 
 
 def strips16k_record(rtdd, dist, rank, world, stream, args):
-    """BASELINE configs[4]: filled in by the row-strip driver (see below)."""
-    return None
+    """BASELINE configs[4]: ONE 16384 x 16384 synthetic image (seed 1005, synthesised on every device), cut
+    into row strips over the N ranks by the native strip frame (rtdd_strip_frame_*: C++ frame loop, H = 16 ghost rows, passes of
+    8 sweeps, staged peer-memory halo exchange over NVLink -- no NCCL on the data path).  Two measurements, each against the
+    one-GPU time of the same run: (i) the finest level alone, 64 sweeps incl. its edge-weight pass, (ii) the full 9-level pyramid
+    (1993 sweeps; its 1.5 ms of coarse levels cannot be split and are solved by every rank).  Strong scaling:
+    efficiency = t(1 GPU) / (N x t(N GPUs)).  Every rank also solves the whole image alone and compares its own rows bit for bit."""
+    from realtimedepthdiffusion_b200 import stripframe, synth_device
+    size, halo, pass_sweeps, l0_sweeps = args.strips_size, 16, 8, 64
+    sf = stripframe.StripFrameRank(size, size, rank, world, halo, pass_sweeps, 1 << 22)
+    ctx = sf.ctx
+    ctx.set_stream(stream)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        bgr, scribble, edited = synth_device.synth_case_device(size, size, 1005, ctx)
+        sf.set_image_device(bgr)
+        sf.set_annotation_device(scribble, edited)
+        if world > 1:
+            sf.connect(dist)
+        solo = rtdd.DepthDiffusion(size, size)
+        solo.set_stream(stream)
+        one = stripframe.StripFrameRank.__new__(stripframe.StripFrameRank)
+        one.ctx, one.rank, one.world, one.rows, one.cols = solo, 0, 1, size, size
+        solo._ck(rtdd._native.lib.rtdd_strip_frame_setup(solo._h, 0, 1, halo, pass_sweeps, 1 << 22))
+        one.set_image_device(bgr)
+        one.set_annotation_device(scribble, edited)
+
+        def timed(who, l0, sync_ranks):
+            def frame():
+                who.reset_first_frame_guess()                      # outside the timed region
+                torch.cuda.synchronize()
+                if sync_ranks:
+                    barrier(dist)
+                ev0.record(stream)
+                if l0:
+                    who.level0(l0)
+                elif who.world == 1:
+                    who.ctx.frame_solve(1000)                      # one GPU: the whole frame as ONE graph, the fastest single-GPU path
+                else:
+                    who.solve(1000)
+                ev1.record(stream)
+                who.ctx.sync()
+                return ev0.elapsed_time(ev1)
+            for _ in range(2):
+                frame()
+            return max_over_ranks(dist, float(np.median([frame() for _ in range(5)])))
+
+        res = {}
+        split, a, b, w0, w1 = sf.rows_of(0)
+        for tag, l0 in (("level0_x64", l0_sweeps), ("full_pyramid", 0)):
+            t_n = timed(sf, l0, True)
+            t_1 = timed(one, l0, False)                            # every rank alone on its own GPU (no exchange): the 1-GPU time
+            mine = sf.plane(ctx.PLANE_DEPTH)[a:b]
+            ref = one.plane(solo.PLANE_DEPTH)[a:b]
+            same = torch.equal(mine.contiguous().view(torch.int32), ref.contiguous().view(torch.int32))
+            if not l0:
+                same = same and torch.equal(sf.plane(ctx.PLANE_DEPTH_U8)[a:b], one.plane(solo.PLANE_DEPTH_U8)[a:b])
+            f = torch.tensor([1.0 if same else 0.0], dtype=torch.float64, device="cuda")
+            if dist is not None:
+                dist.all_reduce(f, op=dist.ReduceOp.MIN)
+            total, per = pixel_sweeps(size, size, ctx.levels)
+            ps = size * size * l0_sweeps if l0 else total
+            res[tag] = {"ms_n_gpus": t_n, "ms_1_gpu": t_1, "speedup": t_1 / t_n, "efficiency": t_1 / (world * t_n),
+                        "Mpixel-sweeps/s": ps / (t_n * 1e-3) / 1e6, "pixel_sweeps": ps, "bit_identical_to_single_gpu": bool(f.item() > 0.5)}
+        res.update({"image": "%dx%d, seed 1005, %d levels" % (size, size, ctx.levels), "n_gpus": world, "scaling": "strong",
+                    "split_levels": [sf.rows_of(l)[0] for l in range(ctx.levels)], "halo_rows": halo, "sweeps_per_pass": pass_sweeps,
+                    "exchange": "staged peer memory (rtdd_strip_push / rtdd_strip_pull over NVLink, CUDA IPC between the ranks' processes)"
+                                if world > 1 else "none (one rank)",
+                    "driver": "rtdd_strip_frame_* (C++ frame loop inside librtdd.so)"})
+        solo.close()
+    sf.close()
+    return res
 
 
 def run_reference(args, dist, rank, world, local):
@@ -502,6 +571,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-batch", action="store_true", help="skip the configs[3] record (256 x 1080p)")
     ap.add_argument("--no-strips", action="store_true", help="skip the configs[4] record (16384^2 row strips)")
+    ap.add_argument("--strips-size", type=int, default=16384, help="side of the configs[4] image")
     ap.add_argument("--seed-offset", type=int, default=0, help="extra offset on the synthetic image seed (diagnostics)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

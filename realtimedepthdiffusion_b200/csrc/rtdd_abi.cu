@@ -435,6 +435,7 @@ int rtdd_create(int rows, int cols, int levels, int device, rtdd_ctx **out)
     p += rtdd_round_up(257 * sizeof(float), 256);
     unsigned int *resWords = (unsigned int *)p;
     ctx->dErrWord = resWords + 63;                     // <= 30 levels use words 0..29
+    ctx->dPeerBadWord = resWords + 62;
     p += 256;
     unsigned int *stripWords = (unsigned int *)p;      // 16 words per level (same offset in every rank's arena)
     p += 2048;
@@ -768,6 +769,8 @@ int rtdd_strip_init(rtdd_ctx *ctx, int level, const float *depth, size_t depthPi
     ctx->launches++;
     L.stripBegin = winBegin; L.stripRows = W.rows; L.stripPair = 0;
     L.stripFused = false;
+    L.stripScan = (winBegin > 0 || winEnd < rows);        // a proper strip: values also arrive from other ranks
+    L.dPeerBad = nullptr;
     L.stripFirstPassAbs = L.stripPassAbs;
     return 0;
 }
@@ -824,6 +827,7 @@ int rtdd_strip_neighbours(rtdd_ctx *ctx, int level, int ownBegin, int ownEnd, in
     L.stripUpWinBegin = aboveWinBegin; L.stripDnWinBegin = belowWinBegin;
     L.stripFused = !ctx->peerStaging;      // staged exchange: the passes stay the plain kernels
     L.stripPushOff = false;
+    if (ctx->peerStaging) { L.stripScan = false; L.dPeerBad = ctx->dPeerBadWord; }      // the push kernels carry the neighbours' verdicts
     if (ctx->peerStaging && halo > RTDD_MAX_HALO) return rtdd_fail(ctx, RTDD_E_ARG, "rtdd_strip_neighbours (halo beyond the staging area)");
     return 0;
 }
@@ -863,7 +867,10 @@ int rtdd_strip_push(rtdd_ctx *ctx, int level)
         dn.rows = H;
         dnFlag = (unsigned int *)(ctx->peerDn + offW) + 5;
     }
-    RTDD_TRY(rtdd::launch_halo_push(ctx->stream, up, dn, L.pitchF, L.dStripWords + 4, upFlag, dnFlag, L.peerSeq + 1u), "rtdd_strip_push");
+    const size_t offBad = (char *)ctx->dPeerBadWord - (char *)ctx->arena;
+    RTDD_TRY(rtdd::launch_halo_push(ctx->stream, up, dn, L.pitchF, L.dStripWords + 4, upFlag, dnFlag, L.peerSeq + 1u, L.dBad, ctx->dPeerBadWord,
+                                    upFlag ? (unsigned int *)(ctx->peerUp + offBad) : nullptr, dnFlag ? (unsigned int *)(ctx->peerDn + offBad) : nullptr),
+             "rtdd_strip_push");
     ctx->launches++;
     return 0;
 }
@@ -955,7 +962,7 @@ static int strip_pass_impl(rtdd_ctx *ctx, int level, int firstSweep, int nsweeps
     for (int i = 0; i < RTDD_MAX_T; i++) pack.w[i] = (i < nsweeps) ? om[firstSweep + i] : 0.0f;
     RtddLevel W = L;
     W.rows = L.stripRows;
-    W.magnitudeCheck = true;           // ghost rows arrive from other GPUs: every pass scans its own tiles (see sweep_cluster_kernel)
+    W.magnitudeCheck = L.stripScan;    // ghost rows from other GPUs without an exchange of verdicts: every pass scans its own tiles (sweep_cluster_kernel)
     const int src = L.stripPair, dst = src ^ 2;
     // on request, the residual of this pass's last sweep (over the whole window; stale ghost rows can only raise it).  Not by
     // default: measured on the 16K level-0 pass, accumulating it costs 4.14 vs 3.87 ms per pass (ncu launch lists,

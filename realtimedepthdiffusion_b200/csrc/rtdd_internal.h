@@ -46,7 +46,10 @@ struct RtddLevel {
     unsigned int *dResidual = nullptr;   // bits of the max-norm of the last sweep's update (rtdd_level_residual)
     unsigned int *dBad = nullptr;        // != 0: the level's start iterate holds a value beyond +-4096 or a NaN (set by the level set-up kernel,
                                          // cleared by a memset before it): the sweeps then divide the IEEE way
-    bool magnitudeCheck = false;         // row-strip windows: ghost rows come from other GPUs, so every pass scans its own tiles instead
+    unsigned int *dPeerBad = nullptr;    // row strips with the staged exchange: the same verdict of the neighbouring ranks (sticky; set by their
+                                         // push kernels over NVLink); null otherwise
+    bool magnitudeCheck = false;         // row-strip windows WITHOUT that exchange of verdicts (NCCL / fused modes): every pass scans its own tiles
+    bool stripScan = false;              // (state of the level's current strip: see rtdd_strip_init / rtdd_strip_neighbours)
 };
 
 // Context-owned images of the frame driver (what main.cpp keeps in GpuMat vectors).
@@ -103,6 +106,7 @@ struct rtdd_ctx {
     char *peerUp = nullptr, *peerDn = nullptr;   // neighbours' arenas (IPC-mapped or same-process), same layout as `arena`
     std::vector<void *> ipcImports;              // arenas mapped by rtdd_ipc_import (closed in rtdd_destroy)
     unsigned int *dErrWord = nullptr;            // device word: RTDD_SPIN_TIMED_OUT once a halo wait gave up
+    unsigned int *dPeerBadWord = nullptr;        // device word: a neighbouring rank saw an iterate beyond +-4096 (sticky, see RtddLevel::dPeerBad)
     unsigned int spinTimeoutMs = 20000;          // rtdd_set_tuning("spin_timeout_ms", ...)
     float *dOmega = nullptr;     // the omega schedule (prefix-stable), dOmegaCap entries
     int dOmegaCap = 0;
@@ -183,7 +187,8 @@ struct HaloRows {
     int rows;
 };
 cudaError_t launch_halo_push(cudaStream_t s, HaloRows up, HaloRows dn, int pitchF, unsigned int *ticket,
-                             unsigned int *upFlag, unsigned int *dnFlag, unsigned int flagValue);
+                             unsigned int *upFlag, unsigned int *dnFlag, unsigned int flagValue,
+                             const unsigned int *ownBad, const unsigned int *peerBadIn, unsigned int *upPeerBad, unsigned int *dnPeerBad);
 cudaError_t launch_halo_pull(cudaStream_t s, HaloRows up, HaloRows dn, int pitchF, const unsigned int *waitUp, const unsigned int *waitDn,
                              unsigned int value, unsigned int *err, unsigned int timeoutMs);
 cudaError_t launch_halo_wait(cudaStream_t s, const unsigned int *waitUp, const unsigned int *waitDn, unsigned int value,

@@ -165,6 +165,11 @@ int rtdd_strip_frame_setup(rtdd_ctx *ctx, int rank, int nranks, int halo, int pa
     sf.rank = rank; sf.nranks = nranks; sf.halo = halo; sf.passSweeps = passSweeps;
     sf.ready = true;
     if (nranks > 1) ctx->peerStaging = true;          // halo rows travel through rtdd_strip_push / rtdd_strip_pull
+    {
+        DeviceGuard2 guard(ctx->device);
+        const int e = rtdd_check(ctx, cudaMemsetAsync(ctx->dPeerBadWord, 0, sizeof(unsigned int), ctx->stream), "rtdd_strip_frame_setup");
+        if (e) return e;
+    }
     return 0;
 }
 
