@@ -285,6 +285,13 @@ int rtdd_frame_solve(rtdd_ctx *ctx, int maxIterations);
  * `coarsestLevel` starts from ITS OWN previous solution with the current annotations re-imposed and runs its scheduled
  * sweeps; finer levels proceed as in rtdd_frame_solve.  coarsestLevel = levels-1 is exactly rtdd_frame_solve. */
 int rtdd_frame_solve_incremental(rtdd_ctx *ctx, int maxIterations, int coarsestLevel);
+/* Extension, NOT parity (the reference always re-solves the whole pyramid, ref: src/main.cpp:232-295): a frame after an edit that
+ * touched level-0 rows [rowBegin, rowEnd) only (a brush stroke).  Coarse levels -- every level below 2^20 pixels, and every level
+ * the band of rows (scaled to the level, widened by `dilation` rows per side) covers by >= 60 % -- are solved whole and equal
+ * the parity frame; on the large levels only the band is re-solved between two frozen rows of the previous solution, and the
+ * rows outside receive the prolongated change of the coarser level.  How far the result is from the parity frame depends on the image
+ * and the edit: tools/live_strokes.py reports it (8-bit identical fraction, mean |delta|).  Needs a previous frame. */
+int rtdd_frame_solve_band(rtdd_ctx *ctx, int maxIterations, int rowBegin, int rowEnd, int dilation);
 /* ref: src/main.cpp:190-230 -- desaturation / haze / defocus of the frame image by the frame's solved depth, written to
  * caller-owned DEVICE planes (BGR u8, byte pitches; any of the three may be NULL).  The defocus summed-area table depends
  * on the image only and is built once per rtdd_frame_set_image, not once per call. */

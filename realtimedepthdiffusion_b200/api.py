@@ -133,6 +133,10 @@ class DepthDiffusion:
     def frame_solve_incremental(self, max_iterations, coarsest_level):
         self._ck(lib.rtdd_frame_solve_incremental(self._h, int(max_iterations), int(coarsest_level)))
 
+    def frame_solve_band(self, max_iterations, row_begin, row_end, dilation=48):
+        """Extension (not parity): re-solve only a band of rows around an edit; see rtdd_frame_solve_band."""
+        self._ck(lib.rtdd_frame_solve_band(self._h, int(max_iterations), int(row_begin), int(row_end), int(dilation)))
+
     def selftest_division(self, n, seed=1, mode=0):
         mism = C.c_ulonglong(0)
         self._ck(lib.rtdd_selftest_division(self._h, int(n), int(seed), int(mode), C.byref(mism)))

@@ -460,6 +460,34 @@ cudaError_t launch_pyrup_depth_rows(cudaStream_t s, const float *src, size_t src
 }
 
 // ---------------------------------------------------------------------------
+// Extension, NOT on the parity path (rtdd_frame_solve_band): the guess of a level when only a band of rows is re-solved.
+// Inside the band: cv::pyrUp of the coarser level's NEW solution, exactly the parity guess.  Outside: the previous solution
+// plus the prolongated CHANGE of the coarser level, pyrUp(new) - pyrUp(old) -- the far-field effect of the edit without
+// re-solving those rows.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+band_prolong_kernel(const float *__restrict__ newC, const float *__restrict__ oldC, size_t pitchC, int srows, int scols,
+                    float *__restrict__ dst, size_t dstPitch, int drows, int dcols, int bandBegin, int bandEnd)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= dcols || y >= drows) return;
+    float *out = (float *)((char *)dst + (size_t)y * dstPitch) + x;
+    const float up = pyrup_px(newC, pitchC, srows, scols, y, x);
+    if (y >= bandBegin && y < bandEnd) *out = up;
+    else *out = __fadd_rn(*out, __fsub_rn(up, pyrup_px(oldC, pitchC, srows, scols, y, x)));
+}
+
+cudaError_t launch_band_prolong(cudaStream_t s, const float *newC, const float *oldC, size_t pitchC, int srows, int scols,
+                                float *dst, size_t dstPitch, int drows, int dcols, int bandBegin, int bandEnd)
+{
+    dim3 block(64, 4);
+    dim3 grid(rtdd_div_up(dcols, block.x), rtdd_div_up(drows, block.y));
+    band_prolong_kernel<<<grid, block, 0, s>>>(newC, oldC, pitchC, srows, scols, dst, dstPitch, drows, dcols, bandBegin, bandEnd);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
 // GpuMat::convertTo(CV_8UC1): round half to even, saturate (ref: src/main.cpp:290)
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)

@@ -477,6 +477,7 @@ int rtdd_destroy(rtdd_ctx *ctx)
     if (ctx->arena) cudaFree(ctx->arena);
     if (ctx->frameArena) cudaFree(ctx->frameArena);
     if (ctx->satScratch) cudaFree(ctx->satScratch);
+    if (ctx->bandArena) cudaFree(ctx->bandArena);
     if (ctx->captureStream) cudaStreamDestroy(ctx->captureStream);
     if (ctx->ownStream) cudaStreamDestroy(ctx->ownStream);
     delete ctx;
@@ -747,8 +748,18 @@ int rtdd_edge_weights(rtdd_ctx *ctx, const float *depth, size_t depthPitch, cons
 // The exchange itself (the (x_k, x_{k-1}) rows next to the strip boundary) is the caller's: NCCL send/recv on
 // rtdd_strip_planes' pointers (realtimedepthdiffusion_b200/strips.py).
 
+static int strip_init_impl(rtdd_ctx *ctx, int level, const float *depth, size_t depthPitch, const uint8_t *scribble, size_t scribblePitch,
+                           const uint8_t *gray, size_t grayPitch, int rows, int cols, int winBegin, int winEnd, int fixRowA, int fixRowB);
+
 int rtdd_strip_init(rtdd_ctx *ctx, int level, const float *depth, size_t depthPitch, const uint8_t *scribble, size_t scribblePitch,
                     const uint8_t *gray, size_t grayPitch, int rows, int cols, int winBegin, int winEnd)
+{
+    return strip_init_impl(ctx, level, depth, depthPitch, scribble, scribblePitch, gray, grayPitch, rows, cols, winBegin, winEnd, -1, -1);
+}
+
+// fixRowA / fixRowB: window-local rows frozen as Dirichlet rows (-1 = none), see rtdd_frame_solve_band
+static int strip_init_impl(rtdd_ctx *ctx, int level, const float *depth, size_t depthPitch, const uint8_t *scribble, size_t scribblePitch,
+                           const uint8_t *gray, size_t grayPitch, int rows, int cols, int winBegin, int winEnd, int fixRowA, int fixRowB)
 {
     if (!ctx) return RTDD_E_ARG;
     if (!ctx->lutLoaded) return rtdd_fail(ctx, RTDD_E_STATE, "rtdd_strip_init (rtdd_load_weights not called)");
@@ -765,11 +776,12 @@ int rtdd_strip_init(rtdd_ctx *ctx, int level, const float *depth, size_t depthPi
     // inside the image simply loses that link, which only affects rows that go stale anyway
     RTDD_TRY(cudaMemsetAsync(L.dBad, 0, sizeof(unsigned int), ctx->stream), "rtdd_strip_init");
     RTDD_TRY(rtdd::launch_level_init(ctx->stream, W, d, depthPitch, scribble + (size_t)winBegin * scribblePitch, scribblePitch,
-                                     gray + (size_t)winBegin * grayPitch, grayPitch, coarsest, threshold, L.x[0]), "rtdd_strip_init");
+                                     gray + (size_t)winBegin * grayPitch, grayPitch, coarsest, threshold, L.x[0], nullptr, fixRowA, fixRowB), "rtdd_strip_init");
     ctx->launches++;
     L.stripBegin = winBegin; L.stripRows = W.rows; L.stripPair = 0;
     L.stripFused = false;
-    L.stripScan = (winBegin > 0 || winEnd < rows);        // a proper strip: values also arrive from other ranks
+    // a proper strip: values also arrive from other ranks (a band between frozen rows is closed: nothing arrives)
+    L.stripScan = (winBegin > 0 && fixRowA < 0) || (winEnd < rows && fixRowB < 0);
     L.dPeerBad = nullptr;
     L.stripFirstPassAbs = L.stripPassAbs;
     return 0;
@@ -1515,6 +1527,84 @@ int rtdd_frame_solve_host_annotation(rtdd_ctx *ctx, const uint8_t *annotationHos
                  "rtdd_frame_solve_host_annotation (download)");
         RTDD_TRY(cudaStreamSynchronize(s), "rtdd_frame_solve_host_annotation");
     }
+    return 0;
+}
+
+// ---- extension, NOT parity: re-solve a band of rows around an edit (live strokes) -------------------------------------------
+// ref for what a frame is: src/main.cpp:232-295; the reference itself always re-solves everything.
+// Level-0 rows [rowBegin, rowEnd) changed (a brush stroke).  Per level, coarse to fine: the band = those rows scaled to the level,
+// widened by `dilation` rows on each side.  Levels the band covers by >= 60 %, and every level small enough for the
+// cluster-resident kernel, are solved whole from the parity guess (prolongation of the new coarser solution + Dirichlet values):
+// up to there the result EQUALS the parity frame.  On the finer levels only the band is re-solved -- same sweeps, same schedule,
+// between two frozen rows of the previous solution -- and the rows outside receive the prolongated change of the coarser level
+// (band_prolong_kernel).  tools/live_strokes.py and tests report how far this is from the parity frame.
+int rtdd_frame_solve_band(rtdd_ctx *ctx, int maxIterations, int rowBegin, int rowEnd, int dilation)
+{
+    if (!ctx) return RTDD_E_ARG;
+    if (!ctx->imageSet || !ctx->lutLoaded) return rtdd_fail(ctx, RTDD_E_STATE, "rtdd_frame_solve_band");
+    if (maxIterations < 0 || rowBegin < 0 || rowEnd > ctx->rows || rowEnd <= rowBegin || dilation < 1) return rtdd_fail(ctx, RTDD_E_ARG, "rtdd_frame_solve_band");
+    DeviceGuard guard(ctx->device);
+    int rc = ensure_omega_table(ctx, maxIterations);
+    if (rc) return rc;
+    const int L = ctx->levels;
+    cudaStream_t s = ctx->stream;
+    if (!ctx->bandArena && L > 1) {
+        size_t total = 0;
+        for (int l = 1; l < L; l++) total += rtdd_round_up(ctx->fl[l].depthPitch * ctx->fl[l].rows, 256);
+        RTDD_TRY(cudaMalloc(&ctx->bandArena, total), "rtdd_frame_solve_band (scratch)");
+        ctx->bandOld.assign(L, nullptr);
+        char *p = (char *)ctx->bandArena;
+        for (int l = 1; l < L; l++) { ctx->bandOld[l] = (float *)p; p += rtdd_round_up(ctx->fl[l].depthPitch * ctx->fl[l].rows, 256); }
+    }
+    for (int l = 1; l < L; l++) {                                                            // main.cpp:249
+        RtddFrameLevel &P = ctx->fl[l - 1], &F = ctx->fl[l];
+        RTDD_TRY(rtdd::launch_pyrdown_annotation(s, P.scribble, P.scribblePitch, P.edited, P.editedPitch, P.rows, P.cols,
+                                                 F.scribble, F.scribblePitch, F.edited, F.editedPitch, F.rows, F.cols), "band: annotation");
+        ctx->launches++;
+    }
+    for (int l = L - 1; l >= 0; l--) {
+        RtddFrameLevel &F = ctx->fl[l];
+        RtddLevel &Lv = ctx->lv[l];
+        const int iters = rtdd_level_iterations(maxIterations, L, l);
+        int b0 = (rowBegin >> l) - dilation, b1 = ((rowEnd + (1 << l) - 1) >> l) + dilation;
+        if (b0 < 0) b0 = 0;
+        if (b1 > F.rows) b1 = F.rows;
+        // below ~1 M pixels a pass costs its latency, not its area (measured: a 54-row band of a 480x270 level took longer than the
+        // whole level inside its graph), so only the large levels are banded
+        const bool whole = (l == L - 1) || (long)Lv.rows * Lv.cols < (1L << 20) || (long)(b1 - b0) * 10 >= (long)F.rows * 6;
+        if (whole) { b0 = 0; b1 = F.rows; }
+        if (l >= 1)         // the finer level needs this level's previous solution for the change it prolongates
+            RTDD_TRY(cudaMemcpy2DAsync(ctx->bandOld[l], F.depthPitch, F.depth, F.depthPitch, (size_t)F.cols * sizeof(float), F.rows, cudaMemcpyDeviceToDevice, s),
+                     "band: keep previous solution");
+        if (l < L - 1) {
+            RtddFrameLevel &C = ctx->fl[l + 1];
+            RTDD_TRY(rtdd::launch_band_prolong(s, C.depth, ctx->bandOld[l + 1], C.depthPitch, C.rows, C.cols, F.depth, F.depthPitch, F.rows, F.cols, b0, b1),
+                     "band: prolongation");
+            ctx->launches++;
+        }
+        RTDD_TRY(rtdd::launch_convert(s, F.edited, F.editedPitch, F.depth, F.depthPitch, F.scribble, F.scribblePitch, F.rows, F.cols), "band: convert");
+        ctx->launches++;
+        if (whole) {
+            rc = rtdd_solve_level(ctx, F.depth, F.depthPitch, F.scribble, F.scribblePitch, F.gray, F.grayPitch, F.rows, F.cols, iters, l);
+            if (rc) return rc;
+            continue;
+        }
+        // the band between two frozen rows (or an image edge)
+        const int w0 = b0 > 0 ? b0 - 1 : 0, w1 = b1 < F.rows ? b1 + 1 : F.rows;
+        rc = strip_init_impl(ctx, l, F.depth, F.depthPitch, F.scribble, F.scribblePitch, F.gray, F.grayPitch, F.rows, F.cols, w0, w1,
+                             b0 > 0 ? 0 : -1, b1 < F.rows ? (w1 - w0 - 1) : -1);
+        if (rc) return rc;
+        const int T = 8;
+        for (int k = 0; k < iters; k += T) {
+            const int n = iters - k < T ? iters - k : T;
+            rc = rtdd_strip_pass(ctx, l, k, n, T);
+            if (rc) return rc;
+        }
+        rc = rtdd_strip_finish(ctx, l, F.depth, F.depthPitch, b0, b1);
+        if (rc) return rc;
+    }
+    RTDD_TRY(rtdd::launch_quantise(s, ctx->fl[0].depth, ctx->fl[0].depthPitch, ctx->depthU8, ctx->depthU8Pitch, ctx->rows, ctx->cols), "band: quantise");
+    ctx->launches++;
     return 0;
 }
 

@@ -128,6 +128,9 @@ struct rtdd_ctx {
     bool frameSatValid = false;        // satScratch holds the summed-area table of the frame image (rtdd_frame_effects)
     // defocus scratch (summed-area tables), grown on demand
     void *satScratch = nullptr; size_t satBytes = 0;
+    // rtdd_frame_solve_band: copies of the levels' previous solutions (levels 1 .. levels-1), same pitches as the frame's depth planes
+    void *bandArena = nullptr;
+    std::vector<float *> bandOld;
 };
 
 int rtdd_fail(rtdd_ctx *ctx, int code, const char *where);
@@ -170,7 +173,8 @@ cudaError_t launch_level_prolong_init(cudaStream_t s, const RtddLevel &L, const 
                                       const uint8_t *gray, size_t grayPitch, int threshold, float *x0, unsigned int *residual);
 cudaError_t launch_level_init(cudaStream_t s, const RtddLevel &L, const float *depth, size_t depthPitch,
                               const uint8_t *scribble, size_t scribblePitch,
-                              const uint8_t *gray, size_t grayPitch, bool coarsest, int threshold, float *x0, unsigned int *residual = nullptr);
+                              const uint8_t *gray, size_t grayPitch, bool coarsest, int threshold, float *x0, unsigned int *residual = nullptr,
+                              int fixRowA = -1, int fixRowB = -1);
 cudaError_t launch_sweep_single(cudaStream_t s, const RtddLevel &L, const float *lut, const float *x, const float *prev,
                                 float *out, float omega, float gamma, bool firstSweep, const SweepTarget *target = nullptr);
 // temporally blocked: T sweeps (x, prev) -> (xOut, prevOut); omegas passed by value (<= RTDD_MAX_T)
@@ -250,6 +254,8 @@ cudaError_t launch_pyrup_depth(cudaStream_t s, const float *src, size_t srcPitch
                                float *dst, size_t dstPitch, int drows, int dcols);
 cudaError_t launch_pyrup_depth_rows(cudaStream_t s, const float *src, size_t srcPitch, int srows, int scols,
                                     float *dst, size_t dstPitch, int drows, int dcols, int rowBegin, int rowEnd);
+cudaError_t launch_band_prolong(cudaStream_t s, const float *newC, const float *oldC, size_t pitchC, int srows, int scols,
+                                float *dst, size_t dstPitch, int drows, int dcols, int bandBegin, int bandEnd);
 cudaError_t launch_quantise(cudaStream_t s, const float *src, size_t srcPitch, uint8_t *dst, size_t dstPitch, int rows, int cols);
 cudaError_t launch_fill_f32(cudaStream_t s, float *dst, size_t pitch, int rows, int cols, float v);
 

@@ -705,6 +705,44 @@ def test_incremental_frame_solve(rtdd):
     inc.close()
 
 
+def test_band_resolve_after_a_stroke_is_close_to_the_parity_frame_and_equal_on_coarse_levels(rtdd):
+    """Extension, not parity (rtdd_frame_solve_band): 1920x1080, one brush stroke after a full frame, band dilation 96 rows.
+    Stated bounds against the parity frame of the same stroke: every level below 2^20 pixels BIT-EQUAL (they are solved whole
+    from the parity guess), the finest level >= 80 % of the 8-bit pixels identical, mean |delta| < 1 grey level, every pixel
+    inside the band within 8 grey levels, Dirichlet values re-imposed."""
+    rows, cols = 1080, 1920
+    bgr, scribble, edited = synth.synth_case(rows, cols, 1002, strokes=8)
+    out = np.zeros((rows, cols), np.uint8)
+    full, band = rtdd.DepthDiffusion(rows, cols), rtdd.DepthDiffusion(rows, cols)
+    for c in (full, band):
+        c.frame_set_image(bgr)
+        c.frame_solve_host(scribble, edited, 1000, out)
+    (x, y, colour, radius) = synth.brush_events(rows, cols, 1003, 1, 1)[0]
+    for c in (full, band):
+        c.frame_paint(x, y, colour, radius)
+    full.frame_solve(1000)
+    h = radius // 2
+    band.frame_solve_band(1000, max(y - h, 0), min(y + h + 1, rows), 96)
+    band.sync()
+    for l in range(1, full.levels):
+        a = full.frame_plane(full.PLANE_DEPTH, l)
+        b = band.frame_plane(band.PLANE_DEPTH, l)
+        assert torch.equal(a.view(torch.int32), b.view(torch.int32)), "level %d (below 2^20 pixels) must equal the parity frame" % l
+    a = full.frame_plane(full.PLANE_DEPTH, 0).cpu().numpy()
+    b = band.frame_plane(band.PLANE_DEPTH, 0).cpu().numpy()
+    qa = full.frame_plane(full.PLANE_DEPTH_U8, 0).cpu().numpy()
+    qb = band.frame_plane(band.PLANE_DEPTH_U8, 0).cpu().numpy()
+    s = band.frame_plane(band.PLANE_SCRIBBLE, 0).cpu().numpy()
+    e = band.frame_plane(band.PLANE_EDITED, 0).cpu().numpy().reshape(rows, cols, 3)
+    assert np.array_equal(b[s == 255], e[..., 0][s == 255].astype(np.float32))
+    assert (qa == qb).mean() >= 0.80, (qa == qb).mean()
+    assert np.abs(a - b).mean() < 1.0, np.abs(a - b).mean()
+    y0, y1 = max(y - h - 96, 0), min(y + h + 1 + 96, rows)
+    assert np.abs(a[y0:y1] - b[y0:y1]).max() < 8.0
+    full.close()
+    band.close()
+
+
 def test_independent_contexts_on_concurrent_streams(rtdd):
     """configs[3]: several images in flight on one GPU, one context + stream each; results equal the one-at-a-time solves."""
     rows, cols, iters = 360, 640, 300

@@ -1,6 +1,8 @@
 """BASELINE configs[1]: 1920x1080 synthetic image, a sequence of brush strokes, one solve frame per stroke.
-Reports ms/frame for the parity path (full fixed-schedule solve, as main.cpp --live does) and for the opt-in
-warm-start incremental re-solve, with the quality delta of the latter against the former.
+Reports ms/frame for the parity path (full fixed-schedule solve, as main.cpp --live does) and for the opt-in extensions --
+the warm start that skips coarse levels (rtdd_frame_solve_incremental) and the band re-solve around the stroke
+(rtdd_frame_solve_band, dilation D rows per level) -- each with its deviation from the parity frame of the same stroke sequence
+(every mode carries its OWN state from frame to frame, so deviations accumulate over the 32 frames).
 python tools/live_strokes.py [strokes] > gpurun_out/live.json"""
 import json
 import os
@@ -21,7 +23,7 @@ events = synth.brush_events(rows, cols, seed + 1, nstrokes, 1)          # one br
 out = np.zeros((rows, cols), np.uint8)
 res = {"workload": "configs[1]: 1920x1080 synthetic image, %d live brush events, one solve frame per event" % nstrokes}
 ctxs = {}
-for mode in ("parity", "incremental_L2", "incremental_L1"):
+for mode in ("parity", "incremental_L2", "incremental_L1", "band_D24", "band_D48", "band_D96"):
     ctx = rtdd.DepthDiffusion(rows, cols)
     ctx.frame_set_image(bgr)
     ctx.frame_solve_host(scribble, edited, 1000, out)
@@ -36,6 +38,9 @@ for (x, y, colour, radius) in events:
         ctx.frame_paint(x, y, colour, radius)
         if mode == "parity":
             ctx.frame_solve(1000)
+        elif mode.startswith("band"):
+            h = radius // 2
+            ctx.frame_solve_band(1000, max(y - h, 0), min(y + h + 1, rows), int(mode.split("_D")[1]))
         else:
             ctx.frame_solve_incremental(1000, int(mode[-1]))
         ev1.record()
@@ -49,5 +54,6 @@ for (x, y, colour, radius) in events:
         ident[mode].append(float((ctx.frame_plane(5, 0) == refq).float().mean()))
 for mode in ctxs:
     res[mode] = {"ms_per_frame_median": float(np.median(times[mode])), "mean_abs_depth_delta_vs_parity": float(np.mean(delta[mode])),
-                 "identical_8bit_fraction_vs_parity": float(np.mean(ident[mode]))}
+                 "identical_8bit_fraction_vs_parity": float(np.mean(ident[mode])),
+                 "identical_8bit_fraction_last_frame": float(ident[mode][-1]), "mean_abs_depth_delta_last_frame": float(delta[mode][-1])}
 print(json.dumps(res))
