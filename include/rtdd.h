@@ -132,7 +132,6 @@ int rtdd_set_sweep_variant(rtdd_ctx *ctx, int variant, int sweepsPerPass);
  * "spin_timeout_ms": device-time limit of a halo wait on a neighbouring rank (default 20000, 0 = for ever); a wait that gives
  *                    up marks the context and the next rtdd_sync returns RTDD_E_PEER instead of the context dying;
  * "resident_warps": target warps per CTA of the cluster-resident kernel (default 8);
- * "resident_one_pixel": 1 (default) levels of <= 16 384 pixels use the one-pixel-per-lane form of the cluster-resident kernel, 0 = never;
  * "pdl": 1 (default) sweep passes are chained with programmatic dependent launch, 0 = plain stream order;
  * "strip_residual": 1 = rtdd_strip_pass also fills the level's residual word (rtdd_level_residual), default 0;
  * "strip_peer_staging": 1 = halo rows of a strip level travel through rtdd_strip_push / rtdd_strip_pull, default 0;

@@ -550,13 +550,6 @@ int rtdd_set_tuning(rtdd_ctx *ctx, const char *key, int value)
         destroy_graphs(ctx);
         return 0;
     }
-    if (strcmp(key, "resident_one_pixel") == 0 && (value == 0 || value == 1)) {
-        rtdd::set_resident1(value);
-        DeviceGuard guard(ctx->device);
-        cudaStreamSynchronize(ctx->stream);
-        destroy_graphs(ctx);
-        return 0;
-    }
     if (strcmp(key, "fused_prolong") == 0 && (value == 0 || value == 1)) {
         g_fusedProlong = value;
         DeviceGuard guard(ctx->device);

@@ -208,7 +208,6 @@ void set_blocked_cluster(int c);
 void set_blocked_grid_cap(int cap);
 void set_resident_warps(int w);
 void set_resident_r1_max_warps(int w);
-void set_resident1(int on);
 void set_pdl(int on);
 int pdl_enabled();
 

@@ -89,17 +89,13 @@ def test_blocked_kernel_forms_agree(rtdd, rows, cols, tile, tma, cluster):
         assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (T, np.abs(got - want).max())
 
 
-@pytest.mark.parametrize("one_pixel", [1, 0])
-@pytest.mark.parametrize("rows,cols", [(1, 1), (2, 5), (9, 40), (31, 128), (33, 97), (67, 120), (135, 240), (64, 64), (128, 128), (128, 130), (256, 256),
-                                       (100, 300), (600, 100), (16, 1000), (400, 30)])
-def test_resident_kernel_forms_agree(rtdd, rows, cols, one_pixel):
-    """Cluster-resident kernels -- four pixels per lane, and one pixel per lane for levels of <= 16 384 pixels --, even and odd sweep
-    counts, incl. the residual by-product."""
+@pytest.mark.parametrize("rows,cols", [(2, 5), (9, 40), (31, 128), (67, 120), (135, 240), (64, 64), (128, 130), (256, 256), (100, 300), (600, 100)])
+def test_resident_kernel_forms_agree(rtdd, rows, cols):
+    """Cluster-resident kernel, even and odd sweep counts, incl. the residual by-product."""
     for iters in (1, 2, 3, 24, 37):
         gray, depth, scribble = random_level(rows, cols, 3 + rows + iters)
         want = ob.solve_level(depth, scribble, gray, iters, 0, 0)
         ctx = rtdd.DepthDiffusion(rows, cols, 1)
-        ctx.set_tuning("resident_one_pixel", one_pixel)
         ctx.set_sweep_variant(3, 0)
         d, s, g = to_dev(depth), to_dev(scribble), to_dev(gray)
         try:
@@ -108,7 +104,6 @@ def test_resident_kernel_forms_agree(rtdd, rows, cols, one_pixel):
             got = to_host(d)
             res = ctx.level_residual(0)
         finally:
-            ctx.set_tuning("resident_one_pixel", 1)
             ctx.close()
         assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (iters, np.abs(got - want).max())
         prev = ob.solve_level(depth, scribble, gray, iters - 1, 0, 0)
