@@ -124,7 +124,7 @@ int rtdd_set_sweep_variant(rtdd_ctx *ctx, int variant, int sweepsPerPass);
 /* Process-wide tuning knobs for experiments (tools/tune_blocked.py); results never change, only speed.
  * "blocked_tile": 0 auto, 64 = 128x64-pixel regions, 34 = 128x32 regions with 2 rows per warp, 32 = 128x32 with 4 rows per warp;
  * "blocked_tma": 3 = TMA-fed persistent thread-block clusters (vertically adjacent CTAs share their edge rows over distributed
- *                shared memory), 1 = TMA-fed persistent single CTAs, 2 (default) = clusters for levels >= 2^22 pixels and
+ *                shared memory), 1 = TMA-fed persistent single CTAs, 2 (default) = clusters for levels >= 2^20 pixels and
  *                single CTAs below (measured), 0 = plain LDG form;
  * "blocked_cluster": CTAs per cluster of the default form (1, 2 (default), 4, 8);
  * "blocked_grid_cap": > 0 limits the persistent form to that many CTAs (tests: every CTA then walks several regions even on

@@ -106,8 +106,9 @@ void destroy_graphs(rtdd_ctx *ctx)
 }
 
 // Sweep-variant policy (all variants are bit-identical; this only decides speed).
-void pick_variant(const rtdd_ctx *ctx, const RtddLevel &L, int iters, int *variant, int *T)
+void pick_variant(const rtdd_ctx *ctx, const RtddLevel &L, int iters, int *variant, int *T, int *form = nullptr)
 {
+    if (form) *form = 0;
     int v = ctx->variant, t = ctx->sweepsPerPass;
     int rR, rC, rB, rW;
     const bool fits = rtdd::resident_plan(L.rows, L.cols, &rR, &rC, &rB, &rW);
@@ -120,10 +121,16 @@ void pick_variant(const rtdd_ctx *ctx, const RtddLevel &L, int iters, int *varia
         t = 0;
     } else if (v == 2) {
         if (t <= 0) {
-            // measured on B200 (tools/tune_frame.py, 4K frame): 8 sweeps per HBM round trip for >= 1 M pixels,
-            // 12 for 256 K..1 M (128x64 tiles), 11 below (128x32 tiles)
+            // 128x64-tile levels (>= 2^18 pixels): sweeps per pass and form from the cost model fitted to tools/tune_levels.py;
+            // smaller levels: 11 (128x32 tiles, measured in round 1)
             const long px = (long)L.rows * L.cols;
-            t = (px >= (1L << 20)) ? 8 : (px >= (1L << 18)) ? 12 : 11;
+            if (px >= (1L << 18)) {
+                int f = 0;
+                rtdd::blocked_plan(L.rows, L.cols, iters, ctx->smCount, &t, &f);
+                if (form) *form = f;
+            } else {
+                t = 11;
+            }
         }
         if (t > RTDD_MAX_T) t = RTDD_MAX_T;
         if (t > iters) t = iters > 0 ? iters : 1;
@@ -164,8 +171,8 @@ bool target_ok(const float *depth, size_t depthPitch)
 int enqueue_sweeps(rtdd_ctx *ctx, cudaStream_t s, int level, int iters, const rtdd::SweepTarget *target, int *kernels, int *resultPlane)
 {
     const RtddLevel &L = ctx->lv[level];
-    int variant, T;
-    pick_variant(ctx, L, iters, &variant, &T);
+    int variant, T, form;
+    pick_variant(ctx, L, iters, &variant, &T, &form);
     std::vector<float> om;
     omega_schedule(iters, om);
     const float gamma = 0.99f;
@@ -192,7 +199,7 @@ int enqueue_sweeps(rtdd_ctx *ctx, cudaStream_t s, int level, int iters, const rt
             for (int i = 0; i < RTDD_MAX_T; i++) pack.w[i] = (i < m) ? om[k + i] : 0.0f;
             const int src = cur, dst = cur ^ 2;
             e = rtdd::launch_sweep_blocked(s, L, ctx->dLut, L.x[src], L.x[src + 1], L.x[dst], L.x[dst + 1], pack, T, m, gamma,
-                                           k == 0, ctx->smCount, (k + m >= iters) ? target : nullptr);
+                                           k == 0, ctx->smCount, (k + m >= iters) ? target : nullptr, nullptr, form);
             n++;
             cur = dst;
         }

@@ -183,7 +183,8 @@ cudaError_t launch_sweep_single(cudaStream_t s, const RtddLevel &L, const float 
 struct OmegaPack { float w[RTDD_MAX_T]; };
 cudaError_t launch_sweep_blocked(cudaStream_t s, const RtddLevel &L, const float *lut, const float *x, const float *prev,
                                  float *xOut, float *prevOut, OmegaPack om, int T, int nsweeps, float gamma, bool firstSweep, int smCount,
-                                 const SweepTarget *target = nullptr, struct HaloPush *push = nullptr);
+                                 const SweepTarget *target = nullptr, struct HaloPush *push = nullptr, int form = 0);
+void blocked_plan(int rows, int cols, int iters, int smCount, int *T, int *form);
 // staged peer exchange: rows of (x_k, x_{k-1}) between this rank's planes and a staging area, plus the completion flags
 struct HaloRows {
     const float *srcX, *srcP;     // first row to copy of each plane (null: nothing on this side)
