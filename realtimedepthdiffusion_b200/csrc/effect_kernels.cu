@@ -28,35 +28,48 @@ __device__ __forceinline__ unsigned int f2u8(float v) { return __float2uint_rz(v
 // summed-area table of the BGR image: S[y][x] = sum over rows < y, cols < x,
 // (rows+1) x (cols+1) uint4 {B, G, R, 0}; u32 wrap-around is harmless because
 // every window sum that is used is < 2^32.
-// Pass A: row prefix sums.  Pass B: column prefix within groups of SAT_G rows.
-// Pass C: exclusive scan of the group totals.  The consumer adds group offsets.
+// Pass 0 (round 2, three small kernels): per group of SAT_G rows, the column sums of the IMAGE strip, prefixed along x = what the
+//         group adds to every table row below it; an exclusive scan over the groups turns them into each group's start values
+//         (1.5 MB at 4K).
+// Pass A: row prefix sums.  Pass B: column prefix within a group, STARTING from the group's start values -- so the table is
+// final and a lookup is ONE 16-byte read per corner (round 1 added a per-group offset at every lookup: 8 reads per pixel).
 // ---------------------------------------------------------------------------
 #define SAT_G 64
 
 __global__ void __launch_bounds__(256)
 sat_rows_kernel(const uint8_t *__restrict__ orig, size_t origPitch, uint4 *__restrict__ sat, int rows, int cols)
 {
-    __shared__ uint3 sWarp[8];
-    __shared__ uint3 sCarry;
+    // one CTA per image row; chunks of 1024 pixels (4 per thread); ONE barrier per chunk: the warp totals are double buffered and
+    // every thread accumulates the running carry itself
+    __shared__ uint3 sWarp[2][8];
     const int y = blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int satPitch = cols + 1;
     uint4 *outRow = sat + (size_t)(y + 1) * satPitch;
     if (y == 0)
         for (int x = threadIdx.x; x <= cols; x += blockDim.x) sat[x] = make_uint4(0, 0, 0, 0);
-    if (threadIdx.x == 0) { outRow[0] = make_uint4(0, 0, 0, 0); sCarry = make_uint3(0, 0, 0); }
-    __syncthreads();
+    if (threadIdx.x == 0) outRow[0] = make_uint4(0, 0, 0, 0);
     const uint8_t *row = orig + (size_t)y * origPitch;
-    for (int base = 0; base < cols; base += 256 * 4) {
+    const bool vec = ((((uintptr_t)orig | origPitch) & 3u) == 0);
+    uint3 carry = make_uint3(0, 0, 0);
+    int buf = 0;
+    for (int base = 0; base < cols; base += 256 * 4, buf ^= 1) {
         const int x0 = base + threadIdx.x * 4;
-        unsigned int b[4], g[4], r[4];
+        unsigned int b[4] = {0, 0, 0, 0}, g[4] = {0, 0, 0, 0}, r[4] = {0, 0, 0, 0};
+        if (vec && x0 + 4 <= cols) {
+            const unsigned int *p = (const unsigned int *)(row + 3 * x0);
+            const unsigned int w[3] = {__ldg(p), __ldg(p + 1), __ldg(p + 2)};
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const int x = x0 + i;
-            const bool in = x < cols;
-            b[i] = in ? __ldg(row + 3 * x) : 0u;
-            g[i] = in ? __ldg(row + 3 * x + 1) : 0u;
-            r[i] = in ? __ldg(row + 3 * x + 2) : 0u;
+            for (int i = 0; i < 12; i++) {
+                const unsigned int v = (w[i >> 2] >> (8 * (i & 3))) & 0xFFu;
+                if (i % 3 == 0) b[i / 3] = v; else if (i % 3 == 1) g[i / 3] = v; else r[i / 3] = v;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int x = x0 + i;
+                if (x < cols) { b[i] = __ldg(row + 3 * x); g[i] = __ldg(row + 3 * x + 1); r[i] = __ldg(row + 3 * x + 2); }
+            }
         }
 #pragma unroll
         for (int i = 1; i < 4; i++) { b[i] += b[i - 1]; g[i] += g[i - 1]; r[i] += r[i - 1]; }
@@ -68,10 +81,15 @@ sat_rows_kernel(const uint8_t *__restrict__ orig, size_t origPitch, uint4 *__res
             const unsigned int tr = __shfl_up_sync(0xFFFFFFFFu, tot.z, d);
             if (lane >= d) { tot.x += tb; tot.y += tg; tot.z += tr; }
         }
-        if (lane == 31) sWarp[warp] = tot;
+        if (lane == 31) sWarp[buf][warp] = tot;
         __syncthreads();
-        uint3 off = sCarry;
-        for (int w = 0; w < warp; w++) { off.x += sWarp[w].x; off.y += sWarp[w].y; off.z += sWarp[w].z; }
+        uint3 off = carry, all = make_uint3(0, 0, 0);
+#pragma unroll
+        for (int w = 0; w < 8; w++) {
+            const uint3 t = sWarp[buf][w];
+            if (w < warp) { off.x += t.x; off.y += t.y; off.z += t.z; }
+            all.x += t.x; all.y += t.y; all.z += t.z;
+        }
         // exclusive prefix of this thread = inclusive warp scan - own total + offsets
         off.x += tot.x - b[3]; off.y += tot.y - g[3]; off.z += tot.z - r[3];
 #pragma unroll
@@ -79,14 +97,84 @@ sat_rows_kernel(const uint8_t *__restrict__ orig, size_t origPitch, uint4 *__res
             const int x = x0 + i;
             if (x < cols) outRow[x + 1] = make_uint4(off.x + b[i], off.y + g[i], off.z + r[i], 0u);
         }
+        carry.x += all.x; carry.y += all.y; carry.z += all.z;
+    }
+}
+
+// Pass 0a: aux[g][x + 1] = sum over the rows of group g of image column x (per channel).  Grid: (column chunks, groups).
+__global__ void __launch_bounds__(128)
+sat_group_colsums_kernel(const uint8_t *__restrict__ orig, size_t origPitch, uint4 *__restrict__ aux, int rows, int cols)
+{
+    const int g = blockIdx.y;
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int satPitch = cols + 1;
+    uint4 *outRow = aux + (size_t)g * satPitch;
+    if (blockIdx.x == 0 && threadIdx.x == 0) outRow[0] = make_uint4(0, 0, 0, 0);
+    if (x0 >= cols) return;
+    const int yBeg = g * SAT_G, yEnd = min(yBeg + SAT_G, rows);
+    const bool vec = ((((uintptr_t)orig | origPitch) & 3u) == 0) && (x0 + 4 <= cols);
+    unsigned int b[4] = {0, 0, 0, 0}, gg[4] = {0, 0, 0, 0}, r[4] = {0, 0, 0, 0};
+#pragma unroll 8
+    for (int y = yBeg; y < yEnd; y++) {
+        const uint8_t *row = orig + (size_t)y * origPitch + 3 * x0;
+        if (vec) {
+            const unsigned int w0 = __ldg((const unsigned int *)row), w1 = __ldg((const unsigned int *)row + 1), w2 = __ldg((const unsigned int *)row + 2);
+            const unsigned int w[3] = {w0, w1, w2};
+#pragma unroll
+            for (int i = 0; i < 12; i++) {
+                const unsigned int v = (w[i >> 2] >> (8 * (i & 3))) & 0xFFu;
+                if (i % 3 == 0) b[i / 3] += v; else if (i % 3 == 1) gg[i / 3] += v; else r[i / 3] += v;
+            }
+        } else {
+            for (int i = 0; i < 4 && x0 + i < cols; i++) { b[i] += __ldg(row + 3 * i); gg[i] += __ldg(row + 3 * i + 1); r[i] += __ldg(row + 3 * i + 2); }
+        }
+    }
+    for (int i = 0; i < 4 && x0 + i < cols; i++) outRow[x0 + i + 1] = make_uint4(b[i], gg[i], r[i], 0u);
+}
+
+// Pass 0b: inclusive prefix along x of every aux row, in place (one CTA per group): aux[g][x] = what group g adds to column x of
+// every table row below it.  Pass 0c (sat_aux_kernel) then scans over the groups.
+__global__ void __launch_bounds__(256)
+sat_group_prefix_kernel(uint4 *__restrict__ aux, int cols)
+{
+    __shared__ uint3 sWarp[8];
+    __shared__ uint3 sCarry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint4 *row = aux + (size_t)blockIdx.x * (cols + 1);
+    if (threadIdx.x == 0) sCarry = make_uint3(0, 0, 0);
+    __syncthreads();
+    for (int base = 1; base <= cols; base += 256 * 4) {
+        const int x0 = base + threadIdx.x * 4;
+        uint4 v[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) v[i] = (x0 + i <= cols) ? row[x0 + i] : make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int i = 1; i < 4; i++) { v[i].x += v[i - 1].x; v[i].y += v[i - 1].y; v[i].z += v[i - 1].z; }
+        uint3 tot = make_uint3(v[3].x, v[3].y, v[3].z);
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned int tb = __shfl_up_sync(0xFFFFFFFFu, tot.x, d);
+            const unsigned int tg = __shfl_up_sync(0xFFFFFFFFu, tot.y, d);
+            const unsigned int tr = __shfl_up_sync(0xFFFFFFFFu, tot.z, d);
+            if (lane >= d) { tot.x += tb; tot.y += tg; tot.z += tr; }
+        }
+        if (lane == 31) sWarp[warp] = tot;
         __syncthreads();
-        if (threadIdx.x == 255) { sCarry = make_uint3(off.x + b[3], off.y + g[3], off.z + r[3]); }
+        uint3 off = sCarry;
+        for (int w = 0; w < warp; w++) { off.x += sWarp[w].x; off.y += sWarp[w].y; off.z += sWarp[w].z; }
+        off.x += tot.x - v[3].x; off.y += tot.y - v[3].y; off.z += tot.z - v[3].z;
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            if (x0 + i <= cols) row[x0 + i] = make_uint4(off.x + v[i].x, off.y + v[i].y, off.z + v[i].z, 0u);
+        __syncthreads();
+        if (threadIdx.x == 255) sCarry = make_uint3(off.x + v[3].x, off.y + v[3].y, off.z + v[3].z);
         __syncthreads();
     }
 }
 
+// Pass B: column prefix inside group g, starting from the group's start values (aux after the exclusive scan of pass 0's totals)
 __global__ void __launch_bounds__(128)
-sat_cols_kernel(uint4 *__restrict__ sat, uint4 *__restrict__ aux, int rows, int cols)
+sat_cols_kernel(uint4 *__restrict__ sat, const uint4 *__restrict__ aux, int rows, int cols)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int g = blockIdx.y;
@@ -94,14 +182,14 @@ sat_cols_kernel(uint4 *__restrict__ sat, uint4 *__restrict__ aux, int rows, int 
     const int satPitch = cols + 1;
     const int yBeg = g * SAT_G + 1;
     const int yEnd = min(yBeg + SAT_G, rows + 1);
-    uint4 acc = make_uint4(0, 0, 0, 0);
+    uint4 acc = __ldg(aux + (size_t)g * satPitch + x);
+#pragma unroll 8
     for (int y = yBeg; y < yEnd; y++) {
         uint4 *p = sat + (size_t)y * satPitch + x;
         const uint4 v = *p;
         acc.x += v.x; acc.y += v.y; acc.z += v.z;
         *p = acc;
     }
-    aux[(size_t)g * satPitch + x] = acc;
 }
 
 __global__ void __launch_bounds__(128)
@@ -111,6 +199,7 @@ sat_aux_kernel(uint4 *__restrict__ aux, int groups, int cols)
     if (x > cols) return;
     const int satPitch = cols + 1;
     uint4 acc = make_uint4(0, 0, 0, 0);
+#pragma unroll 8
     for (int g = 0; g < groups; g++) {
         uint4 *p = aux + (size_t)g * satPitch + x;
         const uint4 v = *p;
@@ -121,10 +210,8 @@ sat_aux_kernel(uint4 *__restrict__ aux, int groups, int cols)
 
 __device__ __forceinline__ uint4 sat_at(const uint4 *__restrict__ sat, const uint4 *__restrict__ aux, int satPitch, int y, int x)
 {
-    if (y == 0) return make_uint4(0, 0, 0, 0);
-    const uint4 a = __ldg(sat + (size_t)y * satPitch + x);
-    const uint4 o = __ldg(aux + (size_t)((y - 1) / SAT_G) * satPitch + x);
-    return make_uint4(a.x + o.x, a.y + o.y, a.z + o.z, 0u);
+    (void)aux;                                   // group start values are folded into the table at build time
+    return __ldg(sat + (size_t)y * satPitch + x);     // row 0 of the table is zero
 }
 
 // ---------------------------------------------------------------------------
@@ -340,9 +427,11 @@ cudaError_t launch_sat_build(cudaStream_t s, void *scratch, const uint8_t *orig,
     uint4 *sat = (uint4 *)scratch;
     uint4 *aux = sat + (size_t)(rows + 1) * (cols + 1);
     const int groups = sat_groups(rows);
+    sat_group_colsums_kernel<<<dim3(rtdd_div_up(rtdd_div_up(cols, 4), 128), groups), 128, 0, s>>>(orig, origPitch, aux, rows, cols);
+    sat_group_prefix_kernel<<<groups, 256, 0, s>>>(aux, cols);
+    sat_aux_kernel<<<rtdd_div_up(cols + 1, 128), 128, 0, s>>>(aux, groups, cols);
     sat_rows_kernel<<<rows, 256, 0, s>>>(orig, origPitch, sat, rows, cols);
     sat_cols_kernel<<<dim3(rtdd_div_up(cols + 1, 128), groups), 128, 0, s>>>(sat, aux, rows, cols);
-    sat_aux_kernel<<<rtdd_div_up(cols + 1, 128), 128, 0, s>>>(aux, groups, cols);
     return cudaGetLastError();
 }
 
@@ -361,7 +450,7 @@ cudaError_t launch_defocus(cudaStream_t s, void *scratch, const uint8_t *orig, s
     if (buildSat) {
         cudaError_t e = launch_sat_build(s, scratch, orig + (size_t)satRow0 * origPitch, origPitch, satRows, cols);
         if (e != cudaSuccess) return e;
-        *launched = 3;
+        *launched = 5;
     }
     *launched += 1;
     if (desat && haze)
