@@ -43,6 +43,10 @@ typedef struct rtdd_ctx rtdd_ctx;
  * One context per GPU; scratch planes for levels l = 0..levels-1 of size
  * floor(rows/2^l) x floor(cols/2^l) in a single HBM arena.  device < 0 = current device. */
 int rtdd_create(int rows, int cols, int levels, int device, rtdd_ctx **out);
+/* A context for one rank of a row-strip frame over `nranks` GPUs (rtdd_strip_frame_*): like rtdd_create, but the scratch planes of
+ * the levels that get split hold only the largest row window a rank keeps (own rows + `halo` ghost rows per side) instead of the
+ * whole level.  Same layout on every rank.  Whole-level calls on such a level return RTDD_E_STATE. */
+int rtdd_create_strip(int rows, int cols, int levels, int device, int nranks, int halo, long long minStripPixels, rtdd_ctx **out);
 /* replaces GPUFreeDeviceMemory(levels)                    ref: include/GPUSolver.h:7, src/GPUSolver.cu:56-71 */
 int rtdd_destroy(rtdd_ctx *ctx);
 /* replaces GPULoadWeights(beta)                           ref: include/GPUSolver.h:8, src/GPUSolver.cu:264-272 */

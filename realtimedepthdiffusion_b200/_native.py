@@ -22,6 +22,7 @@ vp, sz, i32, f32 = C.c_void_p, C.c_size_t, C.c_int, C.c_float
 # name -> (restype, argtypes); every symbol include/rtdd.h declares
 SIGNATURES = {
     "rtdd_create": (i32, [i32, i32, i32, i32, C.POINTER(vp)]),
+    "rtdd_create_strip": (i32, [i32, i32, i32, i32, i32, i32, C.c_longlong, C.POINTER(vp)]),
     "rtdd_destroy": (i32, [vp]),
     "rtdd_load_weights": (i32, [vp, f32]),
     "rtdd_set_stream": (i32, [vp, vp]),

@@ -51,14 +51,17 @@ def _pitch(t):
 class DepthDiffusion:
     """One solver context on one GPU (replaces GPUAllocateDeviceMemory/GPUFreeDeviceMemory state)."""
 
-    def __init__(self, rows, cols, levels=None, device=None, beta=0.4):
+    def __init__(self, rows, cols, levels=None, device=None, beta=0.4, strip=None):
         if not torch.cuda.is_available():
             raise RtddError("no CUDA device: this library has no CPU path")
         self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
         self.rows, self.cols = int(rows), int(cols)
         self.levels = pyramid_levels(rows, cols) if levels is None else int(levels)
         h = C.c_void_p()
-        rc = lib.rtdd_create(self.rows, self.cols, self.levels, self.device.index, C.byref(h))
+        if strip is not None:        # (nranks, halo, min_strip_pixels): window-sized planes for the levels a strip frame splits
+            rc = lib.rtdd_create_strip(self.rows, self.cols, self.levels, self.device.index, int(strip[0]), int(strip[1]), int(strip[2]), C.byref(h))
+        else:
+            rc = lib.rtdd_create(self.rows, self.cols, self.levels, self.device.index, C.byref(h))
         if rc != 0:
             raise RtddError("rtdd_create failed with status %d" % rc)
         self._h = h

@@ -88,12 +88,12 @@ void build_tensor_maps(rtdd_ctx *ctx)
     EncodeTiledFn fn = (EncodeTiledFn)fnp;
     for (auto &L : ctx->lv) {
         bool ok = true;
-        for (int k = 0; k < 4 && ok; k++) ok = encode_plane_map(fn, &L.tmX[k], L.x[k], true, L.pitchF, L.rows, 128, 64);
+        for (int k = 0; k < 4 && ok; k++) ok = encode_plane_map(fn, &L.tmX[k], L.x[k], true, L.pitchF, L.planeRows, 128, 64);
         // byte boxes are 144 wide: see TmaSmem::WB in solver_kernels.cu
-        ok = ok && encode_plane_map(fn, &L.tmLinkR, L.linkR, false, L.pitchB, L.rows, 144, 64);
-        ok = ok && encode_plane_map(fn, &L.tmLinkD, L.linkD, false, L.pitchB, L.rows, 144, 64);
-        ok = ok && encode_plane_map(fn, &L.tmMask, L.mask, false, L.pitchB, L.rows, 144, 64);
-        ok = ok && encode_plane_map(fn, &L.tmLinkD1, L.linkD, false, L.pitchB, L.rows, 144, 65);
+        ok = ok && encode_plane_map(fn, &L.tmLinkR, L.linkR, false, L.pitchB, L.planeRows, 144, 64);
+        ok = ok && encode_plane_map(fn, &L.tmLinkD, L.linkD, false, L.pitchB, L.planeRows, 144, 64);
+        ok = ok && encode_plane_map(fn, &L.tmMask, L.mask, false, L.pitchB, L.planeRows, 144, 64);
+        ok = ok && encode_plane_map(fn, &L.tmLinkD1, L.linkD, false, L.pitchB, L.planeRows, 144, 65);
         L.hasMaps = ok;
     }
 }
@@ -396,7 +396,46 @@ int rtdd_strip_schedule(int iters, int halo, int passSweeps, int level, int *swe
     return n;
 }
 
+static int create_impl(int rows, int cols, int levels, int device, const int *planeRows, rtdd_ctx **out);
+
 int rtdd_create(int rows, int cols, int levels, int device, rtdd_ctx **out)
+{
+    return create_impl(rows, cols, levels, device, nullptr, out);
+}
+
+// A context for ONE rank of a row-strip frame: the planes of the levels that rtdd_plan_strips splits hold only the largest row
+// window any rank keeps (own rows + ghost rows), not the whole level -- 0.9 GB instead of 6.8 GB per rank for a 16384^2 image on
+// 8 GPUs.  All ranks get the same layout (peers address each other's planes by offset).  Whole-level calls on a split level
+// (rtdd_solve_level ...) return RTDD_E_STATE; follow with rtdd_strip_frame_setup using the same rank / halo / minStripPixels.
+int rtdd_create_strip(int rows, int cols, int levels, int device, int nranks, int halo, long long minStripPixels, rtdd_ctx **out)
+{
+    if (!out) return RTDD_E_ARG;
+    *out = nullptr;
+    if (rows < 1 || cols < 1 || levels < 1 || levels > 30 || nranks < 1 || halo < 1 || minStripPixels < 1) return RTDD_E_ARG;
+    std::vector<int> lr(levels), lc(levels), split(levels), ob((size_t)levels * nranks), oe((size_t)levels * nranks), plane(levels);
+    for (int l = 0; l < levels; l++) {
+        lr[l] = (int)((float)rows / powf(2.0f, (float)l)); lc[l] = (int)((float)cols / powf(2.0f, (float)l));
+        if (lr[l] < 1) lr[l] = 1;
+        if (lc[l] < 1) lc[l] = 1;
+    }
+    const int rc = rtdd_plan_strips(lr.data(), lc.data(), levels, nranks, halo, minStripPixels, split.data(), ob.data(), oe.data());
+    if (rc) return rc;
+    for (int l = 0; l < levels; l++) {
+        plane[l] = lr[l];
+        if (nranks > 1 && split[l]) {
+            int mx = 0;
+            for (int r = 0; r < nranks; r++) {
+                const int w0 = ob[l * nranks + r] - halo > 0 ? ob[l * nranks + r] - halo : 0;
+                const int w1 = oe[l * nranks + r] + halo < lr[l] ? oe[l * nranks + r] + halo : lr[l];
+                if (w1 - w0 > mx) mx = w1 - w0;
+            }
+            plane[l] = mx;
+        }
+    }
+    return create_impl(rows, cols, levels, device, plane.data(), out);
+}
+
+static int create_impl(int rows, int cols, int levels, int device, const int *planeRows, rtdd_ctx **out)
 {
     if (!out) return RTDD_E_ARG;
     *out = nullptr;
@@ -427,10 +466,11 @@ int rtdd_create(int rows, int cols, int levels, int device, rtdd_ctx **out)
         L.rows = (int)((float)rows / powf(2.0f, (float)l));
         L.cols = (int)((float)cols / powf(2.0f, (float)l));
         if (L.rows < 1 || L.cols < 1) { L.rows = L.rows < 1 ? 1 : L.rows; L.cols = L.cols < 1 ? 1 : L.cols; }
+        L.planeRows = planeRows ? planeRows[l] : L.rows;
         L.pitchF = (int)rtdd_round_up((size_t)L.cols + 4, 64);
         L.pitchB = (int)rtdd_round_up((size_t)L.cols + 4, 128);
-        total += 4 * rtdd_round_up((size_t)L.pitchF * L.rows * sizeof(float), 256);
-        total += 3 * rtdd_round_up((size_t)L.pitchB * L.rows, 256);
+        total += 4 * rtdd_round_up((size_t)L.pitchF * L.planeRows * sizeof(float), 256);
+        total += 3 * rtdd_round_up((size_t)L.pitchB * L.planeRows, 256);
         total += rtdd_round_up((size_t)8 * RTDD_MAX_HALO * L.pitchF * sizeof(float), 256);     // staged peer exchange (rtdd_strip_push)
     }
     e = cudaMalloc(&ctx->arena, total);
@@ -451,10 +491,10 @@ int rtdd_create(int rows, int cols, int levels, int device, rtdd_ctx **out)
         L.dResidual = resWords + l;
         L.dBad = resWords + 32 + l;
         L.dStripWords = stripWords + 16 * l;
-        for (int k = 0; k < 4; k++) { L.x[k] = (float *)p; p += rtdd_round_up((size_t)L.pitchF * L.rows * sizeof(float), 256); }
-        L.linkR = (uint8_t *)p; p += rtdd_round_up((size_t)L.pitchB * L.rows, 256);
-        L.linkD = (uint8_t *)p; p += rtdd_round_up((size_t)L.pitchB * L.rows, 256);
-        L.mask = (uint8_t *)p;  p += rtdd_round_up((size_t)L.pitchB * L.rows, 256);
+        for (int k = 0; k < 4; k++) { L.x[k] = (float *)p; p += rtdd_round_up((size_t)L.pitchF * L.planeRows * sizeof(float), 256); }
+        L.linkR = (uint8_t *)p; p += rtdd_round_up((size_t)L.pitchB * L.planeRows, 256);
+        L.linkD = (uint8_t *)p; p += rtdd_round_up((size_t)L.pitchB * L.planeRows, 256);
+        L.mask = (uint8_t *)p;  p += rtdd_round_up((size_t)L.pitchB * L.planeRows, 256);
         L.stage = (float *)p;   p += rtdd_round_up((size_t)8 * RTDD_MAX_HALO * L.pitchF * sizeof(float), 256);
     }
     build_tensor_maps(ctx);
@@ -624,6 +664,7 @@ static int edge_pass(rtdd_ctx *ctx, const float *depth, size_t depthPitch, const
     if (!depth || !gray || !level_dims_ok(ctx, level, rows, cols)) return rtdd_fail(ctx, RTDD_E_ARG, where);
     RtddLevel &L = ctx->lv[level];
     if (rows != L.rows || cols != L.cols) return rtdd_fail(ctx, RTDD_E_ARG, where);   // planes are sized per level (ref :42-48)
+    if (L.planeRows < L.rows) return rtdd_fail(ctx, RTDD_E_STATE, where);             // a strip context holds only a window of this level
     // ref: src/GPUSolver.cu:201-202 -- threshold 4, 0 at level 0; :196 -- ungated on the coarsest level
     const bool coarsest = (level == ctx->levels - 1);
     const int threshold = (level == 0) ? 0 : 4;
@@ -642,6 +683,7 @@ int rtdd_solve_level(rtdd_ctx *ctx, float *depth, size_t depthPitch, const uint8
         return rtdd_fail(ctx, RTDD_E_ARG, "rtdd_solve_level");
     RtddLevel &L = ctx->lv[level];
     if (rows != L.rows || cols != L.cols) return rtdd_fail(ctx, RTDD_E_ARG, "rtdd_solve_level");   // planes are sized per level (ref :42-48)
+    if (L.planeRows < L.rows) return rtdd_fail(ctx, RTDD_E_STATE, "rtdd_solve_level (a strip context holds only a window of this level)");
     DeviceGuard guard(ctx->device);
     int rc = ensure_omega_table(ctx, maxIterations);
     if (rc) return rc;
@@ -772,7 +814,8 @@ static int strip_init_impl(rtdd_ctx *ctx, int level, const float *depth, size_t 
     if (!ctx->lutLoaded) return rtdd_fail(ctx, RTDD_E_STATE, "rtdd_strip_init (rtdd_load_weights not called)");
     if (!depth || !scribble || !gray || level < 0 || level >= ctx->levels) return rtdd_fail(ctx, RTDD_E_ARG, "rtdd_strip_init");
     RtddLevel &L = ctx->lv[level];
-    if (rows != L.rows || cols != L.cols || winBegin < 0 || winEnd > rows || winEnd <= winBegin) return rtdd_fail(ctx, RTDD_E_ARG, "rtdd_strip_init");
+    if (rows != L.rows || cols != L.cols || winBegin < 0 || winEnd > rows || winEnd <= winBegin || winEnd - winBegin > L.planeRows)
+        return rtdd_fail(ctx, RTDD_E_ARG, "rtdd_strip_init");
     DeviceGuard guard(ctx->device);
     RtddLevel W = L;
     W.rows = winEnd - winBegin;

@@ -18,6 +18,8 @@
 // planes share pitchB (a multiple of 128).  Padding columns/rows are zero.
 struct RtddLevel {
     int rows = 0, cols = 0;
+    int planeRows = 0;         // rows the level's planes can hold: `rows`, or -- contexts made by rtdd_create_strip -- the largest row
+                               // window any rank keeps of a split level (the same on every rank, so the arenas have one layout)
     int pitchF = 0;            // floats per row of x[] planes
     int pitchB = 0;            // bytes per row of link/mask planes
     float *x[4] = {nullptr, nullptr, nullptr, nullptr};   // rotating iterate planes

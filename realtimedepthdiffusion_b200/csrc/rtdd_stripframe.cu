@@ -214,6 +214,8 @@ struct rtdd_mgpu {
     int n = 0, rows = 0, cols = 0, levels = 0;
     std::vector<int> devices;
     std::vector<rtdd_ctx *> ctx;
+    std::vector<std::vector<rtdd_ctx *>> batchCtx;       // per GPU: contexts for independent images, several in flight (made on first use)
+    float beta = 0.4f;
     std::vector<std::thread> workers;
     std::mutex mu;
     std::condition_variable cvWork, cvDone;
@@ -257,11 +259,25 @@ void mgpu_worker(rtdd_mgpu *m, int r)
         case 1: rc = rtdd_strip_frame_solve(ctx, m->iArg); break;
         case 2: rc = rtdd_strip_frame_level0(ctx, m->iArg); break;
         case 3: {
-            // BASELINE configs[3]: image i -> GPU i mod N, every image a full job from host buffers
-            for (int i = r; i < m->nimages && !rc; i += m->n) {
-                rc = rtdd_frame_set_image(ctx, m->bgrList[i], m->bgrPitch);
-                if (!rc) rc = rtdd_frame_solve_host_annotation(ctx, m->annList[i], m->annPitch, m->iArg, m->outList ? m->outList[i] : nullptr, m->outPitch);
+            // BASELINE configs[3]: image i -> GPU i mod N, every image a full job from host buffers.  Up to 4 images are in flight
+            // per GPU (one context and stream each): the coarse levels keep <= 16 SMs busy, other images' levels fill the rest.
+            const int K = 4;
+            std::vector<rtdd_ctx *> &bc = m->batchCtx[r];
+            while ((int)bc.size() < K && !rc) {
+                rtdd_ctx *c = nullptr;
+                rc = rtdd_create(m->rows, m->cols, m->levels, m->devices[r], &c);
+                if (!rc) rc = rtdd_load_weights(c, m->beta);
+                if (c) bc.push_back(c);
             }
+            int j = 0;
+            for (int i = r; i < m->nimages && !rc; i += m->n, j++) {
+                rtdd_ctx *c = bc[j % K];
+                rc = rtdd_frame_set_image(c, m->bgrList[i], m->bgrPitch);
+                if (!rc) rc = rtdd_frame_solve_host_annotation(c, m->annList[i], m->annPitch, m->iArg, nullptr, 0);
+                if (!rc && m->outList && m->outList[i]) rc = rtdd_frame_read_depth_u8(c, m->outList[i], m->outPitch, 0);
+            }
+            for (rtdd_ctx *c : bc) { const int rs = rtdd_sync(c); if (!rc) rc = rs; }
+            if (rc && !bc.empty()) ctx->err = rtdd_last_error(bc[0]);
             break;
         }
         case 4: rc = rtdd_frame_set_image(ctx, m->hostA, m->pitchA); break;
@@ -334,11 +350,14 @@ int rtdd_mgpu_create(const int *devices, int ndevices, int rows, int cols, int l
     m->levels = levels > 0 ? levels : rtdd_pyramid_levels(rows, cols);
     m->devices.assign(devices, devices + ndevices);
     m->ctx.assign(ndevices, nullptr);
+    m->batchCtx.assign(ndevices, std::vector<rtdd_ctx *>());
+    m->beta = beta;
     m->status.assign(ndevices, 0);
     m->ms.assign(ndevices, 0.0f);
     int rc = 0;
     for (int r = 0; r < ndevices && !rc; r++) {
-        rc = rtdd_create(rows, cols, m->levels, devices[r], &m->ctx[r]);
+        rc = ndevices > 1 ? rtdd_create_strip(rows, cols, m->levels, devices[r], ndevices, halo > 0 ? halo : 16, minStripPixels > 0 ? minStripPixels : (1LL << 22), &m->ctx[r])
+                          : rtdd_create(rows, cols, m->levels, devices[r], &m->ctx[r]);
         if (!rc) rc = rtdd_load_weights(m->ctx[r], beta);
         if (!rc) rc = rtdd_strip_frame_setup(m->ctx[r], r, ndevices, halo > 0 ? halo : 16, passSweeps > 0 ? passSweeps : 8,
                                              minStripPixels > 0 ? minStripPixels : (1LL << 22));
@@ -383,6 +402,7 @@ int rtdd_mgpu_destroy(rtdd_mgpu *m)
     m->cvWork.notify_all();
     for (std::thread &t : m->workers) t.join();
     for (rtdd_ctx *c : m->ctx) if (c) rtdd_destroy(c);
+    for (auto &v : m->batchCtx) for (rtdd_ctx *c : v) if (c) rtdd_destroy(c);
     delete m;
     return 0;
 }

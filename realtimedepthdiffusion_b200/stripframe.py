@@ -15,7 +15,8 @@ from .api import DepthDiffusion, _pitch, _ptr
 
 class StripFrameRank:
     def __init__(self, rows, cols, rank, world, halo=16, pass_sweeps=8, min_strip_pixels=1 << 22, levels=None, device=None):
-        self.ctx = DepthDiffusion(rows, cols, levels=levels, device=device)
+        # window-sized scratch planes for the split levels (0.9 GB instead of 6.8 GB per rank at 16384^2 on 8 GPUs)
+        self.ctx = DepthDiffusion(rows, cols, levels=levels, device=device, strip=(world, halo, min_strip_pixels) if world > 1 else None)
         self.rank, self.world = int(rank), int(world)
         self.rows, self.cols = int(rows), int(cols)
         self.ctx._ck(lib.rtdd_strip_frame_setup(self.ctx._h, self.rank, self.world, int(halo), int(pass_sweeps), int(min_strip_pixels)))
