@@ -23,6 +23,7 @@
 namespace rtdd {
 
 __device__ __forceinline__ unsigned int f2u8(float v) { return __float2uint_rz(v) & 0xFFu; }
+__device__ __forceinline__ int rtdd_div_up_dev(int a, int b) { return (a + b - 1) / b; }
 
 // ---------------------------------------------------------------------------
 // summed-area table of the BGR image: S[y][x] = sum over rows < y, cols < x,
@@ -34,7 +35,7 @@ __device__ __forceinline__ unsigned int f2u8(float v) { return __float2uint_rz(v
 // Pass A: row prefix sums.  Pass B: column prefix within a group, STARTING from the group's start values -- so the table is
 // final and a lookup is ONE 16-byte read per corner (round 1 added a per-group offset at every lookup: 8 reads per pixel).
 // ---------------------------------------------------------------------------
-#define SAT_G 64
+#define SAT_G 16
 
 __global__ void __launch_bounds__(256)
 sat_rows_kernel(const uint8_t *__restrict__ orig, size_t origPitch, uint4 *__restrict__ sat, int rows, int cols)
@@ -172,7 +173,116 @@ sat_group_prefix_kernel(uint4 *__restrict__ aux, int cols)
     }
 }
 
-// Pass B: column prefix inside group g, starting from the group's start values (aux after the exclusive scan of pass 0's totals)
+// Passes A + B in one (round 2): one CTA of 1024 threads per group of SAT_G rows writes the FINAL table rows of its group.  A
+// thread owns 4 columns per 4096-column chunk and keeps their running column sums in registers, starting from the group's start
+// values (aux after passes 0a-0c); per image row it forms the row prefix of its pixels (local prefix, warp scan, one
+// shared-memory hand-off between the 32 warps -- ONE barrier per row, the warp totals are double buffered), adds it to the
+// column sums and stores the table row.  The table is written exactly once (133 MB at 4K) and never read during the build;
+// round 1's two passes wrote it twice and read it once.
+#define SAT_CHUNKS 4                      // 4 x 4096 = 16384 columns at most
+template <int NCH>                        // chunks of 4096 columns a thread carries column sums for (12 registers each)
+__global__ void __launch_bounds__(1024, 1)
+sat_fused_kernel(const uint8_t *__restrict__ orig, size_t origPitch, uint4 *__restrict__ sat, const uint4 *__restrict__ aux, int rows, int cols)
+{
+    __shared__ uint3 sWarp[2][32];
+    const int g = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int satPitch = cols + 1;
+    const int yBeg = g * SAT_G, yEnd = min(yBeg + SAT_G, rows);
+    const int nchunks = rtdd_div_up_dev(cols, 4096);        // <= NCH
+    const bool vecOk = ((((uintptr_t)orig | origPitch) & 3u) == 0);
+    if (g == 0)
+        for (int x = threadIdx.x; x <= cols; x += blockDim.x) sat[x] = make_uint4(0, 0, 0, 0);      // table row 0
+    uint3 acc[NCH][4];
+#pragma unroll
+    for (int c = 0; c < NCH; c++)
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int x = c * 4096 + threadIdx.x * 4 + i;
+            const uint4 v = (c < nchunks && x < cols) ? __ldg(aux + (size_t)g * satPitch + x + 1) : make_uint4(0, 0, 0, 0);
+            acc[c][i] = make_uint3(v.x, v.y, v.z);
+        }
+    int buf = 0;
+    // the 12 pixel bytes of a thread's 4 columns, one row ahead: a row's loads are in flight while the previous row is scanned
+    // (without this a row cost ~4 us: DRAM latency + the scan, serially)
+    auto load_words = [&](int y, int c, unsigned int (&w)[3]) {
+        const int x0 = c * 4096 + threadIdx.x * 4;
+        const uint8_t *row = orig + (size_t)y * origPitch;
+        w[0] = w[1] = w[2] = 0u;
+        if (y >= yEnd || c >= nchunks || x0 >= cols) return;
+        if (vecOk && x0 + 4 <= cols) {
+            const unsigned int *p = (const unsigned int *)(row + 3 * x0);
+            w[0] = __ldg(p); w[1] = __ldg(p + 1); w[2] = __ldg(p + 2);
+        } else {
+            unsigned int bytes[12];
+#pragma unroll
+            for (int i = 0; i < 12; i++) bytes[i] = (x0 + i / 3 < cols) ? (unsigned int)__ldg(row + 3 * x0 + i) : 0u;
+#pragma unroll
+            for (int i = 0; i < 12; i++) w[i >> 2] |= bytes[i] << (8 * (i & 3));
+        }
+    };
+    unsigned int nxt[NCH][3];
+#pragma unroll
+    for (int c = 0; c < NCH; c++) load_words(yBeg, c, nxt[c]);
+    for (int y = yBeg; y < yEnd; y++) {
+        uint4 *outRow = sat + (size_t)(y + 1) * satPitch;
+        if (threadIdx.x == 0) outRow[0] = make_uint4(0, 0, 0, 0);
+        unsigned int cur[NCH][3];
+#pragma unroll
+        for (int c = 0; c < NCH; c++) { cur[c][0] = nxt[c][0]; cur[c][1] = nxt[c][1]; cur[c][2] = nxt[c][2]; }
+#pragma unroll
+        for (int c = 0; c < NCH; c++) load_words(y + 1, c, nxt[c]);
+        uint3 carry = make_uint3(0, 0, 0);
+#pragma unroll
+        for (int c = 0; c < NCH; c++) {
+            if (c >= nchunks) break;
+            const int x0 = c * 4096 + threadIdx.x * 4;
+            unsigned int b[4], gg[4], r[4];
+#pragma unroll
+            for (int i = 0; i < 12; i++) {
+                const unsigned int v = (cur[c][i >> 2] >> (8 * (i & 3))) & 0xFFu;
+                if (i % 3 == 0) b[i / 3] = v; else if (i % 3 == 1) gg[i / 3] = v; else r[i / 3] = v;
+            }
+#pragma unroll
+            for (int i = 1; i < 4; i++) { b[i] += b[i - 1]; gg[i] += gg[i - 1]; r[i] += r[i - 1]; }
+            uint3 tot = make_uint3(b[3], gg[3], r[3]);
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned int tb = __shfl_up_sync(0xFFFFFFFFu, tot.x, d);
+                const unsigned int tg = __shfl_up_sync(0xFFFFFFFFu, tot.y, d);
+                const unsigned int tr = __shfl_up_sync(0xFFFFFFFFu, tot.z, d);
+                if (lane >= d) { tot.x += tb; tot.y += tg; tot.z += tr; }
+            }
+            if (lane == 31) sWarp[buf][warp] = tot;
+            __syncthreads();
+            // every warp scans the 32 warp totals itself: lane l holds the inclusive prefix over warps 0..l
+            uint3 wt = sWarp[buf][lane];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned int tb = __shfl_up_sync(0xFFFFFFFFu, wt.x, d);
+                const unsigned int tg = __shfl_up_sync(0xFFFFFFFFu, wt.y, d);
+                const unsigned int tr = __shfl_up_sync(0xFFFFFFFFu, wt.z, d);
+                if (lane >= d) { wt.x += tb; wt.y += tg; wt.z += tr; }
+            }
+            const unsigned int pbx = __shfl_sync(0xFFFFFFFFu, wt.x, warp > 0 ? warp - 1 : 0);
+            const unsigned int pgx = __shfl_sync(0xFFFFFFFFu, wt.y, warp > 0 ? warp - 1 : 0);
+            const unsigned int prx = __shfl_sync(0xFFFFFFFFu, wt.z, warp > 0 ? warp - 1 : 0);
+            const unsigned int allb = __shfl_sync(0xFFFFFFFFu, wt.x, 31), allg = __shfl_sync(0xFFFFFFFFu, wt.y, 31), allr = __shfl_sync(0xFFFFFFFFu, wt.z, 31);
+            uint3 off = carry;
+            if (warp > 0) { off.x += pbx; off.y += pgx; off.z += prx; }
+            off.x += tot.x - b[3]; off.y += tot.y - gg[3]; off.z += tot.z - r[3];     // exclusive prefix of this thread's first pixel
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                acc[c][i].x += off.x + b[i]; acc[c][i].y += off.y + gg[i]; acc[c][i].z += off.z + r[i];
+                if (x0 + i < cols) outRow[x0 + i + 1] = make_uint4(acc[c][i].x, acc[c][i].y, acc[c][i].z, 0u);
+            }
+            carry.x += allb; carry.y += allg; carry.z += allr;
+            buf ^= 1;
+        }
+    }
+}
+
+// Pass B of the two-pass form (images wider than 16384 columns): column prefix inside group g, starting from the group's start values
 __global__ void __launch_bounds__(128)
 sat_cols_kernel(uint4 *__restrict__ sat, const uint4 *__restrict__ aux, int rows, int cols)
 {
@@ -192,18 +302,36 @@ sat_cols_kernel(uint4 *__restrict__ sat, const uint4 *__restrict__ aux, int rows
     }
 }
 
-__global__ void __launch_bounds__(128)
+// Pass 0c: exclusive scan over the groups, per column: aux[g][x] := sum of aux[g'][x] for g' < g.  One CTA = 32 columns x 8 warps;
+// warp w owns a segment of the groups: segment totals first (independent loads), a shared-memory hand-off, then the running
+// sums (the serial 135-step loop per column of the first version took 70 us at 4K)
+__global__ void __launch_bounds__(256)
 sat_aux_kernel(uint4 *__restrict__ aux, int groups, int cols)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    if (x > cols) return;
+    __shared__ uint3 sTot[8][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int x = blockIdx.x * 32 + lane;
     const int satPitch = cols + 1;
-    uint4 acc = make_uint4(0, 0, 0, 0);
-#pragma unroll 8
-    for (int g = 0; g < groups; g++) {
+    const int seg = (groups + 7) / 8;
+    const int g0 = warp * seg, g1 = min(g0 + seg, groups);
+    uint3 tot = make_uint3(0, 0, 0);
+    if (x <= cols) {
+#pragma unroll 4
+        for (int g = g0; g < g1; g++) {
+            const uint4 v = aux[(size_t)g * satPitch + x];
+            tot.x += v.x; tot.y += v.y; tot.z += v.z;
+        }
+    }
+    sTot[warp][lane] = tot;
+    __syncthreads();
+    if (x > cols) return;
+    uint3 acc = make_uint3(0, 0, 0);
+    for (int w = 0; w < warp; w++) { acc.x += sTot[w][lane].x; acc.y += sTot[w][lane].y; acc.z += sTot[w][lane].z; }
+#pragma unroll 4
+    for (int g = g0; g < g1; g++) {
         uint4 *p = aux + (size_t)g * satPitch + x;
         const uint4 v = *p;
-        *p = acc;                         // exclusive: offset to add to rows of group g
+        *p = make_uint4(acc.x, acc.y, acc.z, 0u);          // exclusive: start values of group g
         acc.x += v.x; acc.y += v.y; acc.z += v.z;
     }
 }
@@ -429,9 +557,17 @@ cudaError_t launch_sat_build(cudaStream_t s, void *scratch, const uint8_t *orig,
     const int groups = sat_groups(rows);
     sat_group_colsums_kernel<<<dim3(rtdd_div_up(rtdd_div_up(cols, 4), 128), groups), 128, 0, s>>>(orig, origPitch, aux, rows, cols);
     sat_group_prefix_kernel<<<groups, 256, 0, s>>>(aux, cols);
-    sat_aux_kernel<<<rtdd_div_up(cols + 1, 128), 128, 0, s>>>(aux, groups, cols);
-    sat_rows_kernel<<<rows, 256, 0, s>>>(orig, origPitch, sat, rows, cols);
-    sat_cols_kernel<<<dim3(rtdd_div_up(cols + 1, 128), groups), 128, 0, s>>>(sat, aux, rows, cols);
+    sat_aux_kernel<<<rtdd_div_up(cols + 1, 32), 256, 0, s>>>(aux, groups, cols);
+    if (cols <= 4096) {
+        sat_fused_kernel<1><<<groups, 1024, 0, s>>>(orig, origPitch, sat, aux, rows, cols);
+    } else if (cols <= 8192) {
+        sat_fused_kernel<2><<<groups, 1024, 0, s>>>(orig, origPitch, sat, aux, rows, cols);
+    } else if (cols <= 4096 * SAT_CHUNKS) {
+        sat_fused_kernel<SAT_CHUNKS><<<groups, 1024, 0, s>>>(orig, origPitch, sat, aux, rows, cols);
+    } else {                 // wider than 16384 columns: the two streaming passes of round 1
+        sat_rows_kernel<<<rows, 256, 0, s>>>(orig, origPitch, sat, rows, cols);
+        sat_cols_kernel<<<dim3(rtdd_div_up(cols + 1, 128), groups), 128, 0, s>>>(sat, aux, rows, cols);
+    }
     return cudaGetLastError();
 }
 
@@ -450,7 +586,7 @@ cudaError_t launch_defocus(cudaStream_t s, void *scratch, const uint8_t *orig, s
     if (buildSat) {
         cudaError_t e = launch_sat_build(s, scratch, orig + (size_t)satRow0 * origPitch, origPitch, satRows, cols);
         if (e != cudaSuccess) return e;
-        *launched = 5;
+        *launched = 4;
     }
     *launched += 1;
     if (desat && haze)
