@@ -33,8 +33,9 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 WORKLOADS = {"8k": (4320, 7680, 1004), "4k": (2160, 3840, 1003), "1080p": (1080, 1920, 1002), "720p": (720, 1280, 1001), "tiny": (203, 317, 77)}
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE level-0 launch (ncu --set full, profiles/r01_ncu_sweep_blocked_L0.txt)
-NCU_TRAFFIC_BYTES_PER_LAUNCH = {"4k": 132.0e6}
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE level-0 launch (ncu --set full, profiles/r02_ncu_L0_cluster_T7_default.txt:
+# 93.5 MB read + 37.9 MB written); workloads without a capture report null
+NCU_TRAFFIC_BYTES_PER_LAUNCH = {"4k": 131.5e6}
 BYTES_PER_PIXEL_SWEEP = 17.0     # x_k 4 + x_{k-1} 4 + x_{k+1} 4 + 4 link indices 4 + mask 1
 
 
