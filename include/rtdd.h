@@ -160,6 +160,12 @@ int rtdd_set_tuning(rtdd_ctx *ctx, const char *key, int value);
 int rtdd_plan_strips(const int *levelRows, const int *levelCols, int levels, int nranks, int halo, long long minStripPixels,
                      int *split, int *ownBegin, int *ownEnd);
 int rtdd_strip_schedule(int iters, int halo, int passSweeps, int level, int *sweepsOfPass, int *exchangeAfter, int capacity);
+/* host only: planeRows[l] = rows the scratch planes of level l hold on every rank of a strip frame (rtdd_create_strip) */
+int rtdd_plan_strip_planes(const int *levelRows, const int *levelCols, int levels, int nranks, int halo, long long minStripPixels, int *planeRows);
+/* host only: how rtdd_solve_level runs `iterations` sweeps of a rows x cols level (>= 2^18 pixels) with the temporally blocked
+ * kernels on a GPU of smCount SMs: sweeps per pass (= per HBM round trip) and whether thread-block clusters of two CTAs sweep
+ * 128 x 128 regions (1) or single CTAs 128 x 64 ones (0).  A cost model fitted to measurements. */
+int rtdd_plan_blocked(int rows, int cols, int iterations, int smCount, int *sweepsPerPass, int *clusterForm);
 int rtdd_strip_init(rtdd_ctx *ctx, int level, const float *depth, size_t depthPitch, const uint8_t *scribble, size_t scribblePitch,
                     const uint8_t *gray, size_t grayPitch, int rows, int cols, int winBegin, int winEnd);
 int rtdd_strip_pass(rtdd_ctx *ctx, int level, int firstSweep, int nsweeps, int haloT);

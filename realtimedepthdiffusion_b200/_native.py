@@ -52,6 +52,8 @@ SIGNATURES = {
     "rtdd_strip_wait": (i32, [vp, i32]),
     "rtdd_plan_strips": (i32, [vp, vp, i32, i32, i32, C.c_longlong, vp, vp, vp]),
     "rtdd_strip_schedule": (i32, [i32, i32, i32, i32, vp, vp, i32]),
+    "rtdd_plan_strip_planes": (i32, [vp, vp, i32, i32, i32, C.c_longlong, vp]),
+    "rtdd_plan_blocked": (i32, [i32, i32, i32, i32, C.POINTER(i32), C.POINTER(i32)]),
     "rtdd_strip_push": (i32, [vp, i32]),
     "rtdd_strip_pull": (i32, [vp, i32]),
     "rtdd_strip_push_enable": (i32, [vp, i32, i32]),

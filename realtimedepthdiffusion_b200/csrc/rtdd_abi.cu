@@ -403,6 +403,39 @@ int rtdd_create(int rows, int cols, int levels, int device, rtdd_ctx **out)
     return create_impl(rows, cols, levels, device, nullptr, out);
 }
 
+// host only: the pass plan of one level solved with the temporally blocked kernels (see rtdd::blocked_plan)
+int rtdd_plan_blocked(int rows, int cols, int iterations, int smCount, int *sweepsPerPass, int *clusterForm)
+{
+    if (rows < 1 || cols < 1 || iterations < 0 || smCount < 1 || !sweepsPerPass || !clusterForm) return RTDD_E_ARG;
+    int T = 0, form = 0;
+    rtdd::blocked_plan(rows, cols, iterations > 0 ? iterations : 1, smCount, &T, &form);
+    *sweepsPerPass = T;
+    *clusterForm = (form == 3) ? 1 : 0;
+    return 0;
+}
+
+// host only: rows the scratch planes of every level must hold on EVERY rank of a row-strip frame (largest window of the split levels)
+int rtdd_plan_strip_planes(const int *levelRows, const int *levelCols, int levels, int nranks, int halo, long long minStripPixels, int *planeRows)
+{
+    if (!levelRows || !levelCols || !planeRows || levels < 1 || nranks < 1 || halo < 1 || minStripPixels < 1) return RTDD_E_ARG;
+    std::vector<int> split(levels), ob((size_t)levels * nranks), oe((size_t)levels * nranks);
+    const int rc = rtdd_plan_strips(levelRows, levelCols, levels, nranks, halo, minStripPixels, split.data(), ob.data(), oe.data());
+    if (rc) return rc;
+    for (int l = 0; l < levels; l++) {
+        planeRows[l] = levelRows[l];
+        if (nranks > 1 && split[l]) {
+            int mx = 0;
+            for (int r = 0; r < nranks; r++) {
+                const int w0 = ob[l * nranks + r] - halo > 0 ? ob[l * nranks + r] - halo : 0;
+                const int w1 = oe[l * nranks + r] + halo < levelRows[l] ? oe[l * nranks + r] + halo : levelRows[l];
+                if (w1 - w0 > mx) mx = w1 - w0;
+            }
+            planeRows[l] = mx;
+        }
+    }
+    return 0;
+}
+
 // A context for ONE rank of a row-strip frame: the planes of the levels that rtdd_plan_strips splits hold only the largest row
 // window any rank keeps (own rows + ghost rows), not the whole level -- 0.9 GB instead of 6.8 GB per rank for a 16384^2 image on
 // 8 GPUs.  All ranks get the same layout (peers address each other's planes by offset).  Whole-level calls on a split level
@@ -412,26 +445,14 @@ int rtdd_create_strip(int rows, int cols, int levels, int device, int nranks, in
     if (!out) return RTDD_E_ARG;
     *out = nullptr;
     if (rows < 1 || cols < 1 || levels < 1 || levels > 30 || nranks < 1 || halo < 1 || minStripPixels < 1) return RTDD_E_ARG;
-    std::vector<int> lr(levels), lc(levels), split(levels), ob((size_t)levels * nranks), oe((size_t)levels * nranks), plane(levels);
+    std::vector<int> lr(levels), lc(levels), plane(levels);
     for (int l = 0; l < levels; l++) {
         lr[l] = (int)((float)rows / powf(2.0f, (float)l)); lc[l] = (int)((float)cols / powf(2.0f, (float)l));
         if (lr[l] < 1) lr[l] = 1;
         if (lc[l] < 1) lc[l] = 1;
     }
-    const int rc = rtdd_plan_strips(lr.data(), lc.data(), levels, nranks, halo, minStripPixels, split.data(), ob.data(), oe.data());
+    const int rc = rtdd_plan_strip_planes(lr.data(), lc.data(), levels, nranks, halo, minStripPixels, plane.data());
     if (rc) return rc;
-    for (int l = 0; l < levels; l++) {
-        plane[l] = lr[l];
-        if (nranks > 1 && split[l]) {
-            int mx = 0;
-            for (int r = 0; r < nranks; r++) {
-                const int w0 = ob[l * nranks + r] - halo > 0 ? ob[l * nranks + r] - halo : 0;
-                const int w1 = oe[l * nranks + r] + halo < lr[l] ? oe[l * nranks + r] + halo : lr[l];
-                if (w1 - w0 > mx) mx = w1 - w0;
-            }
-            plane[l] = mx;
-        }
-    }
     return create_impl(rows, cols, levels, device, plane.data(), out);
 }
 

@@ -97,6 +97,49 @@ def test_native_planning_matches_its_restatement():
     assert [e for _, e in strips.strip_schedule(31, 8, 0, 3)] == [True, True, True, True]
 
 
+def test_strip_plane_rows_are_the_largest_window_and_equal_on_every_rank():
+    """rtdd_create_strip sizes the scratch planes of split levels by rtdd_plan_strip_planes: one layout for all ranks (peers address
+    each other's planes by offset), large enough for every rank's window, full size for the levels every rank solves whole."""
+    import ctypes as C
+    from realtimedepthdiffusion_b200._native import lib
+    rows = cols = 16384
+    levels = 9
+    sizes = [(int(rows / 2.0 ** l), int(cols / 2.0 ** l)) for l in range(levels)]
+    for nranks, halo in ((8, 16), (2, 16), (4, 8), (1, 16)):
+        IntArr = C.c_int * levels
+        lr, lc = IntArr(*[s[0] for s in sizes]), IntArr(*[s[1] for s in sizes])
+        plane = IntArr()
+        assert lib.rtdd_plan_strip_planes(lr, lc, levels, nranks, halo, 1 << 22, plane) == 0
+        plan = strips.plan_strips(sizes, nranks, halo, 1 << 22)
+        for l in range(levels):
+            if plan[l] is None:
+                assert plane[l] == sizes[l][0]
+            else:
+                windows = [min(sizes[l][0], b + halo) - max(0, a - halo) for a, b in plan[l]]
+                assert plane[l] == max(windows) and plane[l] < sizes[l][0]
+    # 16384^2 on 8 GPUs: level 0 keeps 2048 + 2 x 16 rows of 16384
+    assert lib.rtdd_plan_strip_planes(lr, lc, levels, 8, 16, 1 << 22, plane) == 0 and plane[0] == 2080
+
+
+def test_blocked_pass_planner_reproduces_the_measured_optima():
+    """rtdd_plan_blocked (host only): sweeps per pass and form of a large level.  The model behind it was fitted to per-level scans
+    on a B200 (profiles/r02_tune_levels.txt); these are the measured optima it must keep reproducing."""
+    import ctypes as C
+    from realtimedepthdiffusion_b200._native import lib
+    T, cl = C.c_int(), C.c_int()
+
+    def plan(r, c, it):
+        assert lib.rtdd_plan_blocked(r, c, it, 148, C.byref(T), C.byref(cl)) == 0
+        return T.value, cl.value
+    assert plan(2160, 3840, 31) == (7, 1)            # 4K level 0: clusters of 2, 7 sweeps per pass (0.489 ms; 8: 0.500; single CTAs: 0.536)
+    assert plan(1080, 1920, 62) == (16, 1)           # 4K level 1 / 1080p level 0: clusters, 16 (0.262 ms; single CTAs at 8: 0.295)
+    assert plan(540, 960, 125) == (13, 0)            # single CTAs, 13 (0.188 ms; clusters at 16: 0.199)
+    for r, c, it in ((853, 1280, 62), (4320, 7680, 15), (16384, 16384, 3), (2080, 16384, 64), (512, 512, 125)):
+        t, f = plan(r, c, it)
+        assert 4 <= t <= 16 and f in (0, 1)
+    assert lib.rtdd_plan_blocked(0, 10, 5, 148, C.byref(T), C.byref(cl)) == -1
+
+
 def test_strip_schedule_errors_are_negative():
     """rtdd.h: errors are negative (RTDD_E_ARG = -1), never confusable with a pass count."""
     import ctypes as C
