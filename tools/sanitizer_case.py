@@ -15,7 +15,7 @@ from realtimedepthdiffusion_b200.api import to_dev   # noqa: E402
 rows, cols = 203, 317
 bgr, scribble, edited = synth.synth_case(rows, cols, 5)
 out = np.zeros((rows, cols), np.uint8)
-for variant, T, tile, tma in ((1, 0, 0, 1), (2, 5, 64, 1), (2, 8, 64, 0), (2, 7, 34, 0), (2, 4, 32, 0), (3, 0, 0, 1), (0, 0, 0, 1)):
+for variant, T, tile, tma in ((1, 0, 0, 1), (2, 5, 64, 1), (2, 7, 64, 3), (2, 8, 64, 0), (2, 7, 34, 0), (2, 4, 32, 0), (3, 0, 0, 1), (0, 0, 0, 2)):
     ctx = rtdd.DepthDiffusion(rows, cols)
     ctx.set_tuning("blocked_tile", tile)
     ctx.set_tuning("blocked_tma", tma)
@@ -25,6 +25,7 @@ for variant, T, tile, tma in ((1, 0, 0, 1), (2, 5, 64, 1), (2, 8, 64, 0), (2, 7,
     ctx.frame_paint(100, 50, 128, 9)
     ctx.frame_solve(40)
     ctx.frame_solve_incremental(40, 1)
+    ctx.frame_solve_band(40, 40, 60, 8)
     ctx.sync()
     print(variant, T, tile, tma, float(out.mean()), ctx.level_residual(0))
     ctx.set_tuning("blocked_tile", 0)
