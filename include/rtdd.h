@@ -6,7 +6,7 @@
  * context handle, int status returns.  Each entry point names the reference
  * interface it replaces (paths relative to the reference repository).  The
  * reference-named C++ functions of include/GPUSolver.h, GPUImageProcessing.h and
- * GPUDepthEffect.h are thin shims over these (csrc/shims.cpp) that keep the
+ * GPUDepthEffect.h are thin shims over these (csrc/gpu_shims.cpp) that keep the
  * reference's "void + print + continue" error convention and one process-global
  * context.
  *
