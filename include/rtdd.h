@@ -140,7 +140,11 @@ int rtdd_set_sweep_variant(rtdd_ctx *ctx, int variant, int sweepsPerPass);
  * "strip_residual": 1 = rtdd_strip_pass also fills the level's residual word (rtdd_level_residual), default 0;
  * "strip_peer_staging": 1 = halo rows of a strip level travel through rtdd_strip_push / rtdd_strip_pull, default 0;
  * "fused_prolong": 1 = whole-frame path forms a level's guess inside its set-up kernel, default 0 (no faster);
- * "resident_r1_max_warps": largest one-row-per-warp CTA of the cluster-resident kernel (default 32). */
+ * "resident_r1_max_warps": largest one-row-per-warp CTA of the cluster-resident kernel (default 32);
+ * "pass_planner": 1 (default) = passes of their own lengths and halos (rtdd_plan_passes), 0 = one length per level (rtdd_plan_blocked);
+ * "zero_copy_out": 1 (default) = rtdd_frame_solve_host* let the last level-0 pass store the 8-bit map straight into the caller's
+ *                  plane when that is pinned host memory (4-byte aligned base and pitch) and level 0 runs at least 8 sweeps,
+ *                  0 = always the staged copy. */
 int rtdd_set_tuning(rtdd_ctx *ctx, const char *key, int value);
 
 /* ---- row strips: one level of one very large image split across GPUs (BASELINE configs[4]) --------
@@ -166,6 +170,15 @@ int rtdd_plan_strip_planes(const int *levelRows, const int *levelCols, int level
  * kernels on a GPU of smCount SMs: sweeps per pass (= per HBM round trip) and whether thread-block clusters of two CTAs sweep
  * 128 x 128 regions (1) or single CTAs 128 x 64 ones (0).  A cost model fitted to measurements. */
 int rtdd_plan_blocked(int rows, int cols, int iterations, int smCount, int *sweepsPerPass, int *clusterForm);
+/* host only: the passes the level driver actually runs (default; rtdd_set_tuning("pass_planner", 0) returns to one length per
+ * level): the same cost model, every pass with the halo of its own length, lengths chosen by a small dynamic programme
+ * (3840 x 2160 x 31 sweeps: 7, 7, 7, 10).  hostMap = 1: the last pass also stores the 8-bit map into pinned host memory
+ * (rtdd_frame_solve_host*) and is made as long as the tiling allows, so that the transfer hides under its sweeps (7, 8, 16).
+ * Returns the number of passes (the last pass last), negative on error. */
+int rtdd_plan_passes(int rows, int cols, int iterations, int smCount, int hostMap, int *sweepsOfPass, int capacity, int *clusterForm);
+/* The caller's own pass lengths (1..16 sweeps each) for one level of the temporally blocked kernels -- tuning and tests; used
+ * whenever the level is solved with exactly their total, npasses = 0 removes them.  Results do not depend on the plan. */
+int rtdd_set_pass_plan(rtdd_ctx *ctx, int level, const int *sweepsOfPass, int npasses);
 int rtdd_strip_init(rtdd_ctx *ctx, int level, const float *depth, size_t depthPitch, const uint8_t *scribble, size_t scribblePitch,
                     const uint8_t *gray, size_t grayPitch, int rows, int cols, int winBegin, int winEnd);
 int rtdd_strip_pass(rtdd_ctx *ctx, int level, int firstSweep, int nsweeps, int haloT);
@@ -275,7 +288,9 @@ int rtdd_frame_set_image(rtdd_ctx *ctx, const uint8_t *bgrHost, size_t bgrPitch)
 /* One frame: upload level-0 scribble mask + edited image from HOST (main.cpp:236-237),
  * restrict annotations (:249), inject (:257,281), solve every level coarse to fine
  * (:261-288) with maxIterations at the coarsest level, quantise (:290) and download the
- * u8 depth map to HOST (:291).  depthU8Host may be NULL (no download). */
+ * u8 depth map to HOST (:291).  depthU8Host may be NULL (no download).  A depthU8Host in pinned (page-locked) memory with a
+ * 4-byte aligned base and pitch is written by the last sweep pass itself, over PCIe while it computes; any other plane is
+ * filled by a copy after the last pass.  Either way the map is complete when the call returns. */
 int rtdd_frame_solve_host(rtdd_ctx *ctx, const uint8_t *scribbleHost, size_t scribblePitch,
                           const uint8_t *editedHost, size_t editedPitch,
                           int maxIterations, uint8_t *depthU8Host, size_t depthU8Pitch);

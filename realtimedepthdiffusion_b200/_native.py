@@ -54,6 +54,8 @@ SIGNATURES = {
     "rtdd_strip_schedule": (i32, [i32, i32, i32, i32, vp, vp, i32]),
     "rtdd_plan_strip_planes": (i32, [vp, vp, i32, i32, i32, C.c_longlong, vp]),
     "rtdd_plan_blocked": (i32, [i32, i32, i32, i32, C.POINTER(i32), C.POINTER(i32)]),
+    "rtdd_plan_passes": (i32, [i32, i32, i32, i32, i32, C.POINTER(i32), i32, C.POINTER(i32)]),
+    "rtdd_set_pass_plan": (i32, [vp, i32, C.POINTER(i32), i32]),
     "rtdd_strip_push": (i32, [vp, i32]),
     "rtdd_strip_pull": (i32, [vp, i32]),
     "rtdd_strip_push_enable": (i32, [vp, i32, i32]),

@@ -103,6 +103,22 @@ class DepthDiffusion:
     def set_tuning(self, key, value):
         self._ck(lib.rtdd_set_tuning(self._h, key.encode(), int(value)))
 
+    def set_pass_plan(self, level, sweeps_of_pass):
+        """The caller's own pass lengths for one level of the temporally blocked kernels ([] = back to the planner)."""
+        n = len(sweeps_of_pass)
+        arr = (C.c_int * max(n, 1))(*sweeps_of_pass)
+        self._ck(lib.rtdd_set_pass_plan(self._h, int(level), arr, n))
+
+    @staticmethod
+    def plan_passes(rows, cols, iterations, sm_count=148, host_map=False):
+        """(pass lengths, cluster form?) the level driver would use (host only)."""
+        arr = (C.c_int * max(iterations, 1))()
+        form = C.c_int()
+        n = lib.rtdd_plan_passes(rows, cols, iterations, sm_count, 1 if host_map else 0, arr, max(iterations, 1), C.byref(form))
+        if n < 0:
+            raise ValueError("rtdd_plan_passes: %d" % n)
+        return list(arr[:n]), bool(form.value)
+
     # -- GPUSolver -------------------------------------------------------------
     def load_weights(self, beta):
         self._ck(lib.rtdd_load_weights(self._h, beta))
@@ -228,29 +244,32 @@ class DepthDiffusion:
         self._ck(lib.rtdd_frame_read_depth_u8(self._h, C.c_void_p(d.data_ptr()), self.cols, 1 if sync else 0))
         return d
 
+    def _host_map(self, depth_u8_host):
+        """The caller's 8-bit map: a [rows, cols] u8 host plane, rows possibly pitched.  In pinned memory with a 4-byte aligned base
+        and pitch the last sweep pass stores it itself (rtdd.h, "zero_copy_out")."""
+        if depth_u8_host is None:
+            return None, self.cols
+        d = torch.as_tensor(depth_u8_host)
+        assert d.dtype == torch.uint8 and tuple(d.shape) == (self.rows, self.cols) and d.stride(1) == 1 and d.stride(0) >= self.cols
+        return d, d.stride(0)
+
     def frame_solve_host(self, scribble_host, edited_host, max_iterations=1000, depth_u8_host=None):
         s = torch.as_tensor(scribble_host)
         e = torch.as_tensor(edited_host)
         assert s.dtype == torch.uint8 and tuple(s.shape) == (self.rows, self.cols) and s.is_contiguous()
         assert e.dtype == torch.uint8 and tuple(e.shape) == (self.rows, self.cols, 3) and e.is_contiguous()
-        d = depth_u8_host
-        if d is not None:
-            d = torch.as_tensor(d)
-            assert d.dtype == torch.uint8 and tuple(d.shape) == (self.rows, self.cols) and d.is_contiguous()
+        d, dp = self._host_map(depth_u8_host)
         self._ck(lib.rtdd_frame_solve_host(self._h, C.c_void_p(s.data_ptr()), self.cols, C.c_void_p(e.data_ptr()), self.cols * 3,
-                                           int(max_iterations), C.c_void_p(d.data_ptr()) if d is not None else C.c_void_p(0), self.cols))
+                                           int(max_iterations), C.c_void_p(d.data_ptr()) if d is not None else C.c_void_p(0), dp))
         return d
 
     def frame_solve_host_annotation(self, annotation_host, max_iterations=1000, depth_u8_host=None):
         """One frame from the reference's annotation format (ONE u8 plane, 32 = not annotated; ref: src/main.cpp:160-170)."""
         a = torch.as_tensor(annotation_host)
         assert a.dtype == torch.uint8 and tuple(a.shape) == (self.rows, self.cols) and a.is_contiguous()
-        d = depth_u8_host
-        if d is not None:
-            d = torch.as_tensor(d)
-            assert d.dtype == torch.uint8 and tuple(d.shape) == (self.rows, self.cols) and d.is_contiguous()
+        d, dp = self._host_map(depth_u8_host)
         self._ck(lib.rtdd_frame_solve_host_annotation(self._h, C.c_void_p(a.data_ptr()), self.cols, int(max_iterations),
-                                                      C.c_void_p(d.data_ptr()) if d is not None else C.c_void_p(0), self.cols))
+                                                      C.c_void_p(d.data_ptr()) if d is not None else C.c_void_p(0), dp))
         return d
 
     def annotation_ingest(self, annotation, bgr, edited, scribble):

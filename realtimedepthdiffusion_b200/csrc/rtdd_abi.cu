@@ -105,6 +105,9 @@ void destroy_graphs(rtdd_ctx *ctx)
     ctx->graphs.clear();
 }
 
+static int g_zeroCopyOut = 1;           // see host_plane_alias
+static int g_passPlanner = 1;           // 1: passes of their own lengths (rtdd::blocked_plan_passes); 0: one length per level (round-2a behaviour)
+
 // Sweep-variant policy (all variants are bit-identical; this only decides speed).
 void pick_variant(const rtdd_ctx *ctx, const RtddLevel &L, int iters, int *variant, int *T, int *form = nullptr)
 {
@@ -192,16 +195,35 @@ int enqueue_sweeps(rtdd_ctx *ctx, cudaStream_t s, int level, int iters, const rt
         result = iters % 3;
     } else {
         // pair A = planes (0,1), pair B = planes (2,3); each pass reads one pair and writes the other
-        int cur = 0;
-        for (int k = 0; k < iters && e == cudaSuccess; k += T) {
-            const int m = (iters - k < T) ? iters - k : T;
+        // Passes: the caller's own list (rtdd_set_pass_plan), else -- 128x64-tile levels without a forced sweeps-per-pass -- the
+        // planner's (every pass with the halo of its own length), else `T` sweeps per pass with the halo of T throughout.
+        std::vector<int> plan;
+        bool ownHalo = false;
+        const std::vector<int> &forced = ctx->passPlan[level];
+        int forcedSum = 0;
+        for (int m : forced) forcedSum += m;
+        if (!forced.empty() && forcedSum == iters) {
+            plan = forced;
+            ownHalo = true;
+        } else if (g_passPlanner && ctx->sweepsPerPass <= 0 && form != 0) {
+            plan.resize(iters);
+            int f2 = form;
+            const int np = rtdd::blocked_plan_passes(L.rows, L.cols, iters, ctx->smCount, (target && target->u8b) ? 1 : 0, plan.data(), iters, &f2);
+            if (np > 0) { plan.resize(np); form = f2; ownHalo = true; } else plan.clear();
+        }
+        if (plan.empty())
+            for (int k = 0; k < iters; k += T) plan.push_back(iters - k < T ? iters - k : T);
+        int cur = 0, k = 0;
+        for (size_t i = 0; i < plan.size() && e == cudaSuccess; i++) {
+            const int m = plan[i];
             rtdd::OmegaPack pack;
-            for (int i = 0; i < RTDD_MAX_T; i++) pack.w[i] = (i < m) ? om[k + i] : 0.0f;
+            for (int j = 0; j < RTDD_MAX_T; j++) pack.w[j] = (j < m) ? om[k + j] : 0.0f;
             const int src = cur, dst = cur ^ 2;
-            e = rtdd::launch_sweep_blocked(s, L, ctx->dLut, L.x[src], L.x[src + 1], L.x[dst], L.x[dst + 1], pack, T, m, gamma,
+            e = rtdd::launch_sweep_blocked(s, L, ctx->dLut, L.x[src], L.x[src + 1], L.x[dst], L.x[dst + 1], pack, ownHalo ? m : T, m, gamma,
                                            k == 0, ctx->smCount, (k + m >= iters) ? target : nullptr, nullptr, form);
             n++;
             cur = dst;
+            k += m;
         }
         result = cur;
     }
@@ -221,6 +243,7 @@ struct LevelArgs {
     const float *coarse; size_t coarsePitch; int coarseRows, coarseCols;
     const uint8_t *edited; size_t editedPitch;
     bool resetBad;                        // clear the level's out-of-range flag first (the whole-frame graph clears all levels' flags at its start)
+    uint8_t *u8b = nullptr; size_t u8bPitch = 0;   // optional second 8-bit map: device alias of the caller's pinned host plane
 };
 
 // Opt-in (rtdd_set_tuning("fused_prolong", 1)): bit-identical and tested, but measured no faster than the three separate
@@ -251,7 +274,8 @@ int enqueue_level(rtdd_ctx *ctx, cudaStream_t s, const LevelArgs &a, bool captur
     bool direct = false;
     if (a.iters > 0) {
         direct = target_ok(a.depth, a.depthPitch);
-        rtdd::SweepTarget tgt = {direct ? a.depth : nullptr, (int)(a.depthPitch / sizeof(float)), direct ? a.u8 : nullptr, (int)a.u8Pitch, L.dResidual};
+        rtdd::SweepTarget tgt = {direct ? a.depth : nullptr, (int)(a.depthPitch / sizeof(float)), direct ? a.u8 : nullptr, (int)a.u8Pitch, L.dResidual,
+                                 (direct && a.u8) ? a.u8b : nullptr, (int)a.u8bPitch};
         const unsigned int flags = capturing ? cudaEventRecordExternal : cudaEventRecordDefault;
         RTDD_TRY(cudaEventRecordWithFlags(L.evBegin, s, flags), "level event");
         int k = 0;
@@ -411,6 +435,32 @@ int rtdd_plan_blocked(int rows, int cols, int iterations, int smCount, int *swee
     rtdd::blocked_plan(rows, cols, iterations > 0 ? iterations : 1, smCount, &T, &form);
     *sweepsPerPass = T;
     *clusterForm = (form == 3) ? 1 : 0;
+    return 0;
+}
+
+// host only: the passes of one level, each with the halo of its own length (see rtdd::blocked_plan_passes); hostMap = 1: the last
+// pass also stores the 8-bit map into pinned host memory and is made as long as the tiling allows
+int rtdd_plan_passes(int rows, int cols, int iterations, int smCount, int hostMap, int *sweepsOfPass, int capacity, int *clusterForm)
+{
+    if (rows < 1 || cols < 1 || iterations < 1 || smCount < 1 || hostMap < 0 || hostMap > 1 || !sweepsOfPass || capacity < 1 || !clusterForm) return RTDD_E_ARG;
+    int form = 0;
+    const int n = rtdd::blocked_plan_passes(rows, cols, iterations, smCount, hostMap, sweepsOfPass, capacity, &form);
+    if (n <= 0) return RTDD_E_ARG;
+    *clusterForm = (form == 3) ? 1 : 0;
+    return n;
+}
+
+// The caller's own passes for one level of the temporally blocked kernels (tuning, tests): npasses lengths of 1..16 sweeps; a level
+// solved with a different total falls back to the planner.  npasses = 0 removes the list.
+int rtdd_set_pass_plan(rtdd_ctx *ctx, int level, const int *sweepsOfPass, int npasses)
+{
+    if (!ctx || level < 0 || level >= ctx->levels || level >= 32 || npasses < 0 || (npasses > 0 && !sweepsOfPass)) return rtdd_fail(ctx, RTDD_E_ARG, "rtdd_set_pass_plan");
+    for (int i = 0; i < npasses; i++)
+        if (sweepsOfPass[i] < 1 || sweepsOfPass[i] > RTDD_MAX_T) return rtdd_fail(ctx, RTDD_E_ARG, "rtdd_set_pass_plan");
+    DeviceGuard guard(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    destroy_graphs(ctx);
+    ctx->passPlan[level].assign(sweepsOfPass, sweepsOfPass + npasses);
     return 0;
 }
 
@@ -623,6 +673,17 @@ int rtdd_set_tuning(rtdd_ctx *ctx, const char *key, int value)
         DeviceGuard guard(ctx->device);
         cudaStreamSynchronize(ctx->stream);
         destroy_graphs(ctx);
+        return 0;
+    }
+    if (strcmp(key, "pass_planner") == 0 && (value == 0 || value == 1)) {
+        g_passPlanner = value;
+        DeviceGuard guard(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+        destroy_graphs(ctx);
+        return 0;
+    }
+    if (strcmp(key, "zero_copy_out") == 0 && (value == 0 || value == 1)) {
+        g_zeroCopyOut = value;          // graphs are keyed by the host alias: nothing to rebuild
         return 0;
     }
     if (strcmp(key, "strip_residual") == 0 && (value == 0 || value == 1)) {
@@ -1475,8 +1536,27 @@ int rtdd_frame_set_image_device(rtdd_ctx *ctx, const uint8_t *bgrDevice, size_t 
     return 0;
 }
 
-static int frame_solve_from(rtdd_ctx *ctx, int maxIterations, int startLevel)
+// Zero-copy download (rtdd_set_tuning("zero_copy_out", 0/1), default on).  When the caller's 8-bit map lies in pinned (page-locked,
+// device-visible) host memory, the last level-0 pass stores it there itself, next to the context's own copy: the 1 B/px cross PCIe
+// WHILE the pass computes (tools/microbench/zero_copy_rate.cu: SM stores reach 50.5 GB/s against the copy engine's 55.9, and a
+// store stream hidden under 0.08 ms of arithmetic still ends after 0.166 ms), instead of a copy that starts after the last kernel.
+// Pageable host memory, or a plane that is not 4-byte aligned, takes the staged copy as before.
+
+// device-visible alias of a caller's host plane, or null when the plane is pageable / misaligned / zero copy is switched off
+static uint8_t *host_plane_alias(const rtdd_ctx *ctx, uint8_t *host, size_t pitch)
 {
+    if (!g_zeroCopyOut || !host || ((uintptr_t)host & 3u) || (pitch & 3u) || pitch > 0x7FFFFFFFu) return nullptr;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (at.type != cudaMemoryTypeHost || !at.devicePointer) return nullptr;
+    (void)ctx;
+    return (uint8_t *)at.devicePointer;
+}
+
+static int frame_solve_from(rtdd_ctx *ctx, int maxIterations, int startLevel, uint8_t *hostAlias = nullptr, size_t hostAliasPitch = 0,
+                            bool *wroteHost = nullptr)
+{
+    if (wroteHost) *wroteHost = false;
     if (!ctx) return RTDD_E_ARG;
     if (!ctx->imageSet || !ctx->lutLoaded) return rtdd_fail(ctx, RTDD_E_STATE, "rtdd_frame_solve");
     if (maxIterations < 0 || startLevel < 0 || startLevel >= ctx->levels) return rtdd_fail(ctx, RTDD_E_ARG, "rtdd_frame_solve");
@@ -1486,6 +1566,11 @@ static int frame_solve_from(rtdd_ctx *ctx, int maxIterations, int startLevel)
     // the whole frame is ONE graph launch: every plane it touches is owned by the context, so the graph never goes stale
     RtddGraphKey key{};
     key.kind = 2; key.level = startLevel; key.iters = maxIterations; key.variant = ctx->variant; key.T = ctx->sweepsPerPass;
+    // the pass that writes the host map exists only when level 0 sweeps at all and its depth plane takes float4 stores
+    // ... and pays only under a pass of some length (stores into host memory hold the pass up while PCIe drains them)
+    if (hostAlias && !(rtdd_level_iterations(maxIterations, ctx->levels, 0) >= 8 && target_ok(ctx->fl[0].depth, ctx->fl[0].depthPitch))) hostAlias = nullptr;
+    if (hostAlias) { key.p[0] = hostAlias; key.pitch[0] = hostAliasPitch; }
+    if (wroteHost) *wroteHost = hostAlias != nullptr;
     return run_cached_graph(ctx, key, [&](cudaStream_t cs, int *kernels) -> int {
         const int Lc = startLevel;          // coarsest level that is (re)solved; it starts from its current depth plane
         int n = 0;
@@ -1508,6 +1593,7 @@ static int frame_solve_from(rtdd_ctx *ctx, int maxIterations, int startLevel)
             // level 0 also emits the 8-bit map (main.cpp:290) from its last sweep pass
             LevelArgs args{l, iters, F.depth, F.depthPitch, F.scribble, F.scribblePitch, F.gray, F.grayPitch,
                            l == 0 ? ctx->depthU8 : nullptr, l == 0 ? ctx->depthU8Pitch : 0, nullptr, 0, 0, 0, nullptr, 0, false};
+            if (l == 0 && hostAlias) { args.u8b = hostAlias; args.u8bPitch = hostAliasPitch; }
             if (fuseNext) {
                 // this level's guess = prolongation of the level above + its own Dirichlet values, formed by its set-up kernel
                 RtddFrameLevel &C = ctx->fl[l + 1];
@@ -1562,11 +1648,13 @@ int rtdd_frame_solve_host(rtdd_ctx *ctx, const uint8_t *scribbleHost, size_t scr
              "rtdd_frame_solve_host (scribble upload)");                       // main.cpp:236
     RTDD_TRY(cudaMemcpy2DAsync(F.edited, F.editedPitch, editedHost, editedPitch, (size_t)ctx->cols * 3, ctx->rows, cudaMemcpyHostToDevice, s),
              "rtdd_frame_solve_host (edited upload)");                         // main.cpp:237
-    int rc = rtdd_frame_solve(ctx, maxIterations);
+    bool wrote = false;
+    int rc = frame_solve_from(ctx, maxIterations, ctx->levels - 1, host_plane_alias(ctx, depthU8Host, depthU8Pitch), depthU8Pitch, &wrote);
     if (rc) return rc;
     if (depthU8Host) {
-        RTDD_TRY(cudaMemcpy2DAsync(depthU8Host, depthU8Pitch, ctx->depthU8, ctx->depthU8Pitch, (size_t)ctx->cols, ctx->rows, cudaMemcpyDeviceToHost, s),
-                 "rtdd_frame_solve_host (download)");                          // main.cpp:291
+        if (!wrote)
+            RTDD_TRY(cudaMemcpy2DAsync(depthU8Host, depthU8Pitch, ctx->depthU8, ctx->depthU8Pitch, (size_t)ctx->cols, ctx->rows, cudaMemcpyDeviceToHost, s),
+                     "rtdd_frame_solve_host (download)");                      // main.cpp:291
         RTDD_TRY(cudaStreamSynchronize(s), "rtdd_frame_solve_host");
     }
     return 0;
@@ -1591,11 +1679,13 @@ int rtdd_frame_solve_host_annotation(rtdd_ctx *ctx, const uint8_t *annotationHos
     RTDD_TRY(rtdd::launch_annotation_ingest(s, ctx->annot, ctx->annotPitch, ctx->bgr, ctx->bgrPitch, F.edited, F.editedPitch, F.scribble, F.scribblePitch,
                                             ctx->rows, ctx->cols), "rtdd_frame_solve_host_annotation (ingest)");
     ctx->launches++;
-    int rc = rtdd_frame_solve(ctx, maxIterations);
+    bool wrote = false;
+    int rc = frame_solve_from(ctx, maxIterations, ctx->levels - 1, host_plane_alias(ctx, depthU8Host, depthU8Pitch), depthU8Pitch, &wrote);
     if (rc) return rc;
     if (depthU8Host) {
-        RTDD_TRY(cudaMemcpy2DAsync(depthU8Host, depthU8Pitch, ctx->depthU8, ctx->depthU8Pitch, (size_t)ctx->cols, ctx->rows, cudaMemcpyDeviceToHost, s),
-                 "rtdd_frame_solve_host_annotation (download)");
+        if (!wrote)
+            RTDD_TRY(cudaMemcpy2DAsync(depthU8Host, depthU8Pitch, ctx->depthU8, ctx->depthU8Pitch, (size_t)ctx->cols, ctx->rows, cudaMemcpyDeviceToHost, s),
+                     "rtdd_frame_solve_host_annotation (download)");
         RTDD_TRY(cudaStreamSynchronize(s), "rtdd_frame_solve_host_annotation");
     }
     return 0;

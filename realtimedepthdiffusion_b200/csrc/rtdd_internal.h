@@ -113,6 +113,7 @@ struct rtdd_ctx {
     float *dOmega = nullptr;     // the omega schedule (prefix-stable), dOmegaCap entries
     int dOmegaCap = 0;
     int sweepsPerPass = 0;       // 0 auto
+    std::vector<int> passPlan[32];   // per level: the caller's own pass lengths (rtdd_set_pass_plan; empty = the planner's)
     std::map<RtddGraphKey, RtddGraph> graphs;
     std::vector<RtddLevelTiming> captureTiming;   // filled by enqueue_level while a graph is being captured
     unsigned long long launches = 0;
@@ -151,6 +152,7 @@ struct SweepTarget {
     float *x; int pitchX;        // floats per row; null = keep the library's own planes
     uint8_t *u8; int pitchU8;    // may be null
     unsigned int *res;           // may be null: receives the bits of max |x_K - x_{K-1}| (atomicMax)
+    uint8_t *u8b; int pitchU8b;  // may be null: a second copy of the 8-bit map (device alias of a pinned host plane); needs u8 != null
 };
 // fused multi-GPU halo push (solver_kernels.cu); plain data, filled by rtdd_strip_pass
 struct HaloPush {
@@ -187,6 +189,7 @@ cudaError_t launch_sweep_blocked(cudaStream_t s, const RtddLevel &L, const float
                                  float *xOut, float *prevOut, OmegaPack om, int T, int nsweeps, float gamma, bool firstSweep, int smCount,
                                  const SweepTarget *target = nullptr, struct HaloPush *push = nullptr, int form = 0);
 void blocked_plan(int rows, int cols, int iters, int smCount, int *T, int *form);
+int blocked_plan_passes(int rows, int cols, int iters, int smCount, int hostMap, int *passes, int capacity, int *form);
 // staged peer exchange: rows of (x_k, x_{k-1}) between this rank's planes and a staging area, plus the completion flags
 struct HaloRows {
     const float *srcX, *srcP;     // first row to copy of each plane (null: nothing on this side)

@@ -89,6 +89,86 @@ def test_blocked_kernel_forms_agree(rtdd, rows, cols, tile, tma, cluster):
         assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (T, np.abs(got - want).max())
 
 
+@pytest.mark.parametrize("tma,cluster", [(3, 2), (1, 1), (0, 1)])
+@pytest.mark.parametrize("rows,cols", [(203, 317), (300, 700)])
+def test_passes_of_mixed_lengths_bit_exact_vs_oracle(rtdd, rows, cols, tma, cluster):
+    """rtdd_set_pass_plan: every pass runs with the halo of its own length (what the level driver's planner does from 2^18 pixels
+    on); all lengths 1..16, each followed and preceded by a different one, in the three tiling forms."""
+    iters = 36
+    plans = ([1, 2, 3, 4, 5, 6, 7, 8], [9, 10, 11, 6], [12, 13, 11], [14, 15, 7], [16, 16, 4], [7, 7, 7, 10, 5])
+    gray, depth, scribble = random_level(rows, cols, 11 + rows)
+    want = ob.solve_level(depth, scribble, gray, iters, 1, 2)
+    for plan in plans:
+        assert sum(plan) == iters
+        ctx = rtdd.DepthDiffusion(rows * 2, cols * 2, 3)
+        ctx.set_tuning("blocked_tile", 64)
+        ctx.set_tuning("blocked_tma", tma)
+        ctx.set_tuning("blocked_cluster", cluster)
+        ctx.set_sweep_variant(2, 0)
+        ctx.set_pass_plan(1, plan)
+        d, s, g = to_dev(depth), to_dev(scribble), to_dev(gray)
+        try:
+            ctx.matrix_free_solver(d, s, g, iters, 1)
+            ctx.sync()
+            got = to_host(d)
+            _, _, launches = ctx.level_sweep_ms(1)
+        finally:
+            ctx.set_tuning("blocked_tile", 0)
+            ctx.set_tuning("blocked_tma", 2)
+            ctx.set_tuning("blocked_cluster", 2)
+            ctx.close()
+        assert launches == len(plan)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (plan, np.abs(got - want).max())
+
+
+@pytest.mark.parametrize("rows,cols", [(540, 960), (541, 963), (301, 450)])
+def test_map_stored_by_the_last_pass_into_pinned_host_memory(rtdd, rows, cols):
+    """rtdd_frame_solve_host*: a pinned, 4-byte aligned caller plane is written by the last level-0 pass itself (over PCIe, next to
+    the context's own copy); pageable, misaligned or switched-off planes take the staged copy.  Same bytes every way, over two
+    frames (the second starts from the first's state, like main.cpp), and rows beyond `cols` of a pitched plane stay untouched."""
+    bgr, scribble, edited = synth.synth_case(rows, cols, 31 + rows)
+    annot = synth.annotation_plane(scribble, edited)
+    ev = synth.brush_events(rows, cols, 5, 1, 6)
+    s2, e2 = synth.paint_events(bgr, ev, scribble.copy(), edited.copy())
+    annot2 = synth.annotation_plane(s2, e2)
+    pitch4 = (cols + 3) // 4 * 4 + 8
+
+    def run(kind):
+        ctx = rtdd.DepthDiffusion(rows, cols)
+        ctx.frame_set_image(bgr)
+        if kind == "pageable":
+            out = torch.full((rows, cols), 77, dtype=torch.uint8)
+        elif kind == "pinned-off":
+            out = torch.full((rows, cols), 77, dtype=torch.uint8).pin_memory()
+            ctx.set_tuning("zero_copy_out", 0)
+        elif kind == "pinned-pitched":
+            out = torch.full((rows, pitch4), 77, dtype=torch.uint8).pin_memory()[:, :cols]
+        elif kind == "pinned-misaligned":
+            flat = torch.full((rows * cols + 8,), 77, dtype=torch.uint8).pin_memory()
+            out = flat[1:1 + rows * cols].view(rows, cols)
+        else:
+            out = torch.full((rows, cols), 77, dtype=torch.uint8).pin_memory()
+        try:
+            a = ctx.frame_solve_host_annotation(annot, 1000, out).clone()
+            dev_a = ctx.frame_read_depth_u8(torch.empty((rows, cols), dtype=torch.uint8)).clone()
+            b = ctx.frame_solve_host(s2, e2, 1000, out).clone()
+            whole = out._base if out._base is not None and kind == "pinned-pitched" else None
+            margin = whole[:, cols:].clone() if whole is not None else None
+        finally:
+            ctx.set_tuning("zero_copy_out", 1)
+            ctx.close()
+        return a.numpy(), dev_a.numpy(), b.numpy(), margin
+
+    base = run("pageable")
+    assert np.array_equal(base[0], base[1]) and not np.array_equal(base[0], base[2])
+    for kind in ("pinned", "pinned-off", "pinned-pitched", "pinned-misaligned"):
+        got = run(kind)
+        for i in range(3):
+            assert np.array_equal(got[i], base[i]), (kind, i, int((got[i] != base[i]).sum()))
+        if got[3] is not None:
+            assert bool((got[3] == 77).all()), kind
+
+
 @pytest.mark.parametrize("rows,cols", [(2, 5), (9, 40), (31, 128), (67, 120), (135, 240), (64, 64), (128, 130), (256, 256), (100, 300), (600, 100)])
 def test_resident_kernel_forms_agree(rtdd, rows, cols):
     """Cluster-resident kernel, even and odd sweep counts, incl. the residual by-product."""

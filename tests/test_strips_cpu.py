@@ -140,6 +140,37 @@ def test_blocked_pass_planner_reproduces_the_measured_optima():
     assert lib.rtdd_plan_blocked(0, 10, 5, 148, C.byref(T), C.byref(cl)) == -1
 
 
+def test_pass_planner_with_passes_of_their_own_lengths():
+    """rtdd_plan_passes (host only): what the level driver runs by default -- every pass with the halo of its own length.  Pinned to
+    the plans measured on a B200 (profiles/r02_tune_passes.txt): 3840x2160 x 31 as (7, 7, 7, 10) 0.466 ms against 0.484 for 4 x 7 + 3;
+    with the 8-bit map stored into pinned host memory by the last pass, that pass is as long as the tiling allows (end to end
+    2.01 ms with (7, 8, 16) against 2.07 with (7, 7, 7, 10))."""
+    import ctypes as C
+    import random
+    from realtimedepthdiffusion_b200 import DepthDiffusion as D
+    from realtimedepthdiffusion_b200._native import lib
+    assert D.plan_passes(2160, 3840, 31) == ([7, 7, 7, 10], True)
+    assert D.plan_passes(2160, 3840, 31, host_map=True) == ([7, 8, 16], True)
+    assert D.plan_passes(1080, 1920, 62) == ([14, 16, 16, 16], True)
+    assert D.plan_passes(4320, 7680, 15) == ([7, 8], True)
+    assert D.plan_passes(4320, 7680, 15, host_map=True) == ([15], True)
+    assert D.plan_passes(540, 960, 125)[1] is False
+    rng = random.Random(5)
+    for _ in range(200):
+        r, c, it = rng.randint(1, 5000), rng.randint(1, 9000), rng.randint(1, 300)
+        for host in (False, True):
+            plan, _ = D.plan_passes(r, c, it, sm_count=rng.choice((1, 2, 74, 132, 148)), host_map=host)
+            assert sum(plan) == it and all(1 <= m <= 16 for m in plan), (r, c, it, plan)
+            if host:
+                assert plan[-1] == min(16, it)
+            else:
+                assert plan == sorted(plan)
+    buf, f = (C.c_int * 4)(), C.c_int()
+    assert lib.rtdd_plan_passes(2160, 3840, 31, 148, 0, buf, 2, C.byref(f)) < 0          # capacity too small
+    assert lib.rtdd_plan_passes(2160, 3840, 0, 148, 0, buf, 4, C.byref(f)) == -1
+    assert lib.rtdd_plan_passes(2160, 3840, 31, 148, 2, buf, 4, C.byref(f)) == -1
+
+
 def test_strip_schedule_errors_are_negative():
     """rtdd.h: errors are negative (RTDD_E_ARG = -1), never confusable with a pass count."""
     import ctypes as C

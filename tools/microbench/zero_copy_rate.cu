@@ -1,0 +1,79 @@
+// Microbenchmark (B200 + host): SM loads/stores straight to pinned host memory over PCIe against the copy engine, for one
+// 3840x2160 u8 plane (8.3 MB) — the per-frame download (8-bit depth map) and upload (annotation plane) of the end-to-end call.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o zero_copy_rate zero_copy_rate.cu && ./zero_copy_rate
+// Store patterns: 4 B per lane (what the last level-0 pass writes per row: one 128-byte line per warp), 16 B per lane, and
+// 4 B per lane issued by few CTAs slowly (a store stream spread over ~100 us like the last pass).
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+__global__ void store4(uint32_t *dst, size_t n, uint32_t v)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = v + (uint32_t)i;
+}
+__global__ void store16(uint4 *dst, size_t n, uint32_t v)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = make_uint4(v, v + 1, v + 2, (uint32_t)i);
+}
+__global__ void load16(const uint4 *src, size_t n, uint4 *sink)
+{
+    uint4 acc = make_uint4(0, 0, 0, 0);
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        uint4 t = src[i];
+        acc.x ^= t.x; acc.y ^= t.y; acc.z ^= t.z; acc.w ^= t.w;
+    }
+    if (acc.x == 0x12345u) sink[0] = acc;
+}
+// the same store stream with arithmetic between the stores (about `spin` dependent FMAs per store)
+__global__ void store4_slow(uint32_t *dst, size_t n, uint32_t v, int spin, float *sink)
+{
+    float a = (float)threadIdx.x;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        for (int k = 0; k < spin; k++) a = __fmaf_rn(a, 1.0001f, 0.5f);
+        dst[i] = v + (uint32_t)i;
+    }
+    if (a == 12345.0f) sink[0] = a;
+}
+
+template <class F> static float timeit(F f, int reps)
+{
+    cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+    f(); cudaDeviceSynchronize();
+    cudaEventRecord(a);
+    for (int r = 0; r < reps; r++) f();
+    cudaEventRecord(b); cudaEventSynchronize(b);
+    float ms; cudaEventElapsedTime(&ms, a, b);
+    return ms / reps;
+}
+
+int main()
+{
+    const size_t bytes = 3840ull * 2160ull;
+    void *host, *dev, *sink;
+    cudaHostAlloc(&host, bytes, cudaHostAllocMapped | cudaHostAllocPortable);
+    cudaMalloc(&dev, bytes); cudaMalloc(&sink, 64);
+    void *hostDev; cudaHostGetDevicePointer(&hostDev, host, 0);
+    const int reps = 20;
+    float t;
+    t = timeit([&] { cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, 0); }, reps);
+    printf("copy engine D2H            %.3f ms  %.1f GB/s\n", t, bytes / t * 1e-6);
+    t = timeit([&] { cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, 0); }, reps);
+    printf("copy engine H2D            %.3f ms  %.1f GB/s\n", t, bytes / t * 1e-6);
+    for (int grid : {148, 592, 2368}) {
+        t = timeit([&] { store4<<<grid, 256>>>((uint32_t *)hostDev, bytes / 4, 7u); }, reps);
+        printf("SM store 4B/lane  grid %4d  %.3f ms  %.1f GB/s\n", grid, t, bytes / t * 1e-6);
+        t = timeit([&] { store16<<<grid, 256>>>((uint4 *)hostDev, bytes / 16, 7u); }, reps);
+        printf("SM store 16B/lane grid %4d  %.3f ms  %.1f GB/s\n", grid, t, bytes / t * 1e-6);
+        t = timeit([&] { load16<<<grid, 256>>>((const uint4 *)hostDev, bytes / 16, (uint4 *)sink); }, reps);
+        printf("SM load 16B/lane  grid %4d  %.3f ms  %.1f GB/s\n", grid, t, bytes / t * 1e-6);
+    }
+    // device-memory reference for the slow store stream, then the same stream to the host
+    for (int spin : {64, 256, 1024}) {
+        float td = timeit([&] { store4_slow<<<148, 512>>>((uint32_t *)dev, bytes / 4, 7u, spin, (float *)sink); }, reps);
+        float th = timeit([&] { store4_slow<<<148, 512>>>((uint32_t *)hostDev, bytes / 4, 7u, spin, (float *)sink); }, reps);
+        printf("store stream with %4d FMAs per store: to HBM %.3f ms, to pinned host %.3f ms\n", spin, td, th);
+    }
+    cudaError_t e = cudaDeviceSynchronize();
+    printf("status: %s\n", cudaGetErrorString(e));
+    return e != cudaSuccess;
+}
