@@ -305,6 +305,11 @@ int rtdd_frame_read_depth_u8(rtdd_ctx *ctx, uint8_t *depthU8Host, size_t depthU8
 /* Same frame with the annotation planes already on the device (paint with
  * rtdd_frame_paint); nothing crosses PCIe. */
 int rtdd_frame_solve(rtdd_ctx *ctx, int maxIterations);
+/* The live loop's frame (ref: src/main.cpp:232-295 with the strokes painted on the device by rtdd_frame_paint): rtdd_frame_solve
+ * followed by the download of the 8-bit map (main.cpp:291) into HOST memory -- stored by the last level-0 pass itself when
+ * depthU8Host is pinned and 4-byte aligned ("zero_copy_out"), a copy after the last pass otherwise.  Returns after the map is
+ * complete. */
+int rtdd_frame_solve_download(rtdd_ctx *ctx, int maxIterations, uint8_t *depthU8Host, size_t depthU8Pitch);
 /* Warm-start incremental re-solve for live strokes (extension; the reference's only warm start is the coarsest depth
  * plane persisting between frames, ref: src/main.cpp:257).  Levels coarser than `coarsestLevel` are skipped; level
  * `coarsestLevel` starts from ITS OWN previous solution with the current annotations re-imposed and runs its scheduled

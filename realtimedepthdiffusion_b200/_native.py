@@ -38,6 +38,7 @@ SIGNATURES = {
     "rtdd_level_residual": (i32, [vp, i32, C.POINTER(f32)]),
     "rtdd_solve_level_converge": (i32, [vp, vp, sz, vp, sz, vp, sz, i32, i32, i32, f32, i32, i32, C.POINTER(i32), C.POINTER(f32)]),
     "rtdd_frame_solve_incremental": (i32, [vp, i32, i32]),
+    "rtdd_frame_solve_download": (i32, [vp, i32, vp, sz]),
     "rtdd_frame_solve_band": (i32, [vp, i32, i32, i32, i32]),
     "rtdd_selftest_division": (i32, [vp, C.c_ulonglong, C.c_ulonglong, i32, C.POINTER(C.c_ulonglong)]),
     "rtdd_strip_init": (i32, [vp, i32, vp, sz, vp, sz, vp, sz, i32, i32, i32, i32]),

@@ -281,6 +281,12 @@ class DepthDiffusion:
     def frame_solve(self, max_iterations=1000):
         self._ck(lib.rtdd_frame_solve(self._h, int(max_iterations)))
 
+    def frame_solve_download(self, depth_u8_host, max_iterations=1000):
+        """The live loop's frame: strokes already painted on the device (frame_paint), 8-bit map into host memory."""
+        d, dp = self._host_map(depth_u8_host)
+        self._ck(lib.rtdd_frame_solve_download(self._h, int(max_iterations), C.c_void_p(d.data_ptr()), dp))
+        return d
+
     def frame_paint(self, x, y, color, radius):
         self._ck(lib.rtdd_frame_paint(self._h, int(x), int(y), int(color), int(radius)))
 

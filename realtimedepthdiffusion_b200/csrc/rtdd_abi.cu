@@ -1660,6 +1660,23 @@ int rtdd_frame_solve_host(rtdd_ctx *ctx, const uint8_t *scribbleHost, size_t scr
     return 0;
 }
 
+int rtdd_frame_solve_download(rtdd_ctx *ctx, int maxIterations, uint8_t *depthU8Host, size_t depthU8Pitch)
+{
+    if (!ctx) return RTDD_E_ARG;
+    if (!ctx->imageSet) return rtdd_fail(ctx, RTDD_E_STATE, "rtdd_frame_solve_download");
+    if (!depthU8Host || depthU8Pitch < (size_t)ctx->cols) return rtdd_fail(ctx, RTDD_E_ARG, "rtdd_frame_solve_download");
+    DeviceGuard guard(ctx->device);
+    cudaStream_t s = ctx->stream;
+    bool wrote = false;
+    int rc = frame_solve_from(ctx, maxIterations, ctx->levels - 1, host_plane_alias(ctx, depthU8Host, depthU8Pitch), depthU8Pitch, &wrote);
+    if (rc) return rc;
+    if (!wrote)
+        RTDD_TRY(cudaMemcpy2DAsync(depthU8Host, depthU8Pitch, ctx->depthU8, ctx->depthU8Pitch, (size_t)ctx->cols, ctx->rows, cudaMemcpyDeviceToHost, s),
+                 "rtdd_frame_solve_download");                                 // main.cpp:291
+    RTDD_TRY(cudaStreamSynchronize(s), "rtdd_frame_solve_download");
+    return 0;
+}
+
 // The same frame fed with the reference's persistent annotation format (ref: src/main.cpp:160-170): ONE gray plane, 32 = not
 // annotated.  1 B/px crosses PCIe instead of the 4 B/px of scribble + 3-channel edited; the expansion main.cpp does on
 // the host runs on the device (annotation_ingest_kernel).  Results are identical to rtdd_frame_solve_host on the planes

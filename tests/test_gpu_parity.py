@@ -152,18 +152,22 @@ def test_map_stored_by_the_last_pass_into_pinned_host_memory(rtdd, rows, cols):
             a = ctx.frame_solve_host_annotation(annot, 1000, out).clone()
             dev_a = ctx.frame_read_depth_u8(torch.empty((rows, cols), dtype=torch.uint8)).clone()
             b = ctx.frame_solve_host(s2, e2, 1000, out).clone()
+            # third frame the live loop's way: the stroke painted on the device, rtdd_frame_solve_download
+            x, y, colour, radius = synth.brush_events(rows, cols, 6, 1, 1)[0]
+            ctx.frame_paint(x, y, colour, radius)
+            c = ctx.frame_solve_download(out, 1000).clone()
             whole = out._base if out._base is not None and kind == "pinned-pitched" else None
             margin = whole[:, cols:].clone() if whole is not None else None
         finally:
             ctx.set_tuning("zero_copy_out", 1)
             ctx.close()
-        return a.numpy(), dev_a.numpy(), b.numpy(), margin
+        return a.numpy(), dev_a.numpy(), b.numpy(), margin, c.numpy()
 
     base = run("pageable")
-    assert np.array_equal(base[0], base[1]) and not np.array_equal(base[0], base[2])
+    assert np.array_equal(base[0], base[1]) and not np.array_equal(base[0], base[2]) and not np.array_equal(base[2], base[4])
     for kind in ("pinned", "pinned-off", "pinned-pitched", "pinned-misaligned"):
         got = run(kind)
-        for i in range(3):
+        for i in (0, 1, 2, 4):
             assert np.array_equal(got[i], base[i]), (kind, i, int((got[i] != base[i]).sum()))
         if got[3] is not None:
             assert bool((got[3] == 77).all()), kind

@@ -23,7 +23,8 @@ events = synth.brush_events(rows, cols, seed + 1, nstrokes, 1)          # one br
 out = np.zeros((rows, cols), np.uint8)
 res = {"workload": "configs[1]: 1920x1080 synthetic image, %d live brush events, one solve frame per event" % nstrokes}
 ctxs = {}
-for mode in ("parity", "incremental_L2", "incremental_L1", "band_D24", "band_D48", "band_D96"):
+pinned = torch.zeros((rows, cols), dtype=torch.uint8).pin_memory()
+for mode in ("parity", "parity_with_download", "incremental_L2", "incremental_L1", "band_D24", "band_D48", "band_D96"):
     ctx = rtdd.DepthDiffusion(rows, cols)
     ctx.frame_set_image(bgr)
     ctx.frame_solve_host(scribble, edited, 1000, out)
@@ -38,6 +39,8 @@ for (x, y, colour, radius) in events:
         ctx.frame_paint(x, y, colour, radius)
         if mode == "parity":
             ctx.frame_solve(1000)
+        elif mode == "parity_with_download":
+            ctx.frame_solve_download(pinned, 1000)             # main.cpp:291 included: the map lands in pinned host memory
         elif mode.startswith("band"):
             h = radius // 2
             ctx.frame_solve_band(1000, max(y - h, 0), min(y + h + 1, rows), int(mode.split("_D")[1]))
