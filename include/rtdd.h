@@ -359,7 +359,8 @@ int rtdd_strip_frame_effects(rtdd_ctx *ctx, uint8_t *desat, size_t desatPitch, u
 /* ---- several GPUs from ONE process: one host thread per GPU inside the library (what a C++ host like main.cpp links) -------
  * rtdd_mgpu_create makes one context per listed device, enables peer access between neighbours and wires their arenas.
  * halo / passSweeps / minStripPixels <= 0 select the defaults (16 / 8 / 2^22).  Every call below runs on all GPUs concurrently
- * and returns when all have finished; *msDevice (may be NULL) = the slowest rank's device time. */
+ * and returns when all have finished; *msDevice (may be NULL) = the slowest rank's device time.  A handle serves ONE calling
+ * thread at a time (the command slot is shared by the worker threads); different handles are independent. */
 typedef struct rtdd_mgpu rtdd_mgpu;
 int rtdd_mgpu_create(const int *devices, int ndevices, int rows, int cols, int levels, float beta, int halo, int passSweeps,
                      long long minStripPixels, rtdd_mgpu **out);
