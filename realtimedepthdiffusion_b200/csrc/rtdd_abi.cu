@@ -1546,10 +1546,13 @@ int rtdd_frame_set_image_device(rtdd_ctx *ctx, const uint8_t *bgrDevice, size_t 
 static uint8_t *host_plane_alias(const rtdd_ctx *ctx, uint8_t *host, size_t pitch)
 {
     if (!g_zeroCopyOut || !host || ((uintptr_t)host & 3u) || (pitch & 3u) || pitch > 0x7FFFFFFFu) return nullptr;
-    cudaPointerAttributes at;
+    cudaPointerAttributes at, last;
     if (cudaPointerGetAttributes(&at, host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
     if (at.type != cudaMemoryTypeHost || !at.devicePointer) return nullptr;
-    (void)ctx;
+    // the last byte of the plane must be page-locked too (a caller may have registered only part of a larger buffer)
+    const uint8_t *end = host + (size_t)(ctx->rows - 1) * pitch + (size_t)ctx->cols - 1;
+    if (cudaPointerGetAttributes(&last, end) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (last.type != cudaMemoryTypeHost || (const uint8_t *)last.devicePointer - (const uint8_t *)at.devicePointer != end - host) return nullptr;
     return (uint8_t *)at.devicePointer;
 }
 
