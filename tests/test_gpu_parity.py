@@ -362,6 +362,20 @@ def test_call_order_and_argument_errors(rtdd):
     ctx.matrix_free_solver(d, s, g, 3, 0)
     ctx.sync()
     assert ctx.launch_count >= 2
+    # rtdd_set_pass_plan: level and pass lengths are checked; a plan whose total differs from the level's sweeps is simply not used
+    for level, plan in ((1, [3]), (-1, [3]), (0, [0, 3]), (0, [17])):
+        with pytest.raises(rtdd.RtddError):
+            ctx.set_pass_plan(level, plan)
+    ctx.set_pass_plan(0, [2, 2])
+    ctx.set_sweep_variant(2, 0)
+    ctx.matrix_free_solver(d, s, g, 3, 0)
+    ctx.set_pass_plan(0, [])
+    # rtdd_frame_solve_download before an image was set, and without a destination
+    with pytest.raises(rtdd.RtddError):
+        ctx.frame_solve_download(torch.zeros((64, 64), dtype=torch.uint8), 10)
+    with pytest.raises(rtdd.RtddError):
+        ctx.set_tuning("zero_copy_out", 2)
+    ctx.sync()
     ctx.close()
 
 
