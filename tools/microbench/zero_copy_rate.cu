@@ -35,6 +35,50 @@ __global__ void store4_slow(uint32_t *dst, size_t n, uint32_t v, int spin, float
     if (a == 12345.0f) sink[0] = a;
 }
 
+// The 8-bit map of the last pass the way the sweep kernel produces it: 148 persistent CTAs, per region `spin` FMAs per thread, then a
+// 112 x 56 byte tile goes to the host -- MODE 0: one 32-bit store per lane and row (what the kernel does), MODE 1: the tile parked in
+// shared memory and handed to the bulk-copy engine row by row (cp.async.bulk.global.shared::cta, 112 bytes per row)
+template <int MODE>
+__global__ void __launch_bounds__(512, 1) tile_stream(uint8_t *dst, int pitch, int rowsTotal, int regions, int spin, float *sink)
+{
+    __shared__ __align__(128) unsigned char stage[64 * 128];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float a = (float)threadIdx.x;
+    const int tilesX = pitch / 112;
+    for (int it = 0; it < regions; it++) {
+        const int tile = it * gridDim.x + blockIdx.x;
+        const int x0 = (tile % tilesX) * 112, y0 = ((tile / tilesX) * 56) % (rowsTotal - 64);
+        for (int k = 0; k < spin; k++) a = __fmaf_rn(a, 1.0001f, 0.5f);
+        __syncthreads();
+        if (MODE == 0) {
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                const int row = warp * 4 + r;
+                if (row < 56 && lane < 28) *(unsigned int *)(dst + (size_t)(y0 + row) * pitch + x0 + 4 * lane) = (unsigned int)tile + lane;
+            }
+        } else {
+            if (lane < 4) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            __syncwarp();
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                const int row = warp * 4 + r;
+                if (lane < 28) *(unsigned int *)(stage + row * 128 + 4 * lane) = (unsigned int)tile + lane;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane < 4) {
+                const int row = warp * 4 + lane;
+                if (row < 56)
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                 ::"l"(__cvta_generic_to_global(dst + (size_t)(y0 + row) * pitch + x0)), "r"((unsigned int)__cvta_generic_to_shared(stage + row * 128)), "r"(112u) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        }
+    }
+    if (MODE == 1 && lane < 4) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (a == 12345.0f) sink[0] = a;
+}
+
 template <class F> static float timeit(F f, int reps)
 {
     cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
@@ -72,6 +116,13 @@ int main()
         float td = timeit([&] { store4_slow<<<148, 512>>>((uint32_t *)dev, bytes / 4, 7u, spin, (float *)sink); }, reps);
         float th = timeit([&] { store4_slow<<<148, 512>>>((uint32_t *)hostDev, bytes / 4, 7u, spin, (float *)sink); }, reps);
         printf("store stream with %4d FMAs per store: to HBM %.3f ms, to pinned host %.3f ms\n", spin, td, th);
+    }
+    // 148 CTAs x 9 regions x (112 x 56) bytes = 8.35 MB per launch: one 4K map
+    for (int spin : {0, 4000, 8000, 16000}) {
+        float tn = timeit([&] { tile_stream<0><<<148, 512>>>((uint8_t *)dev, 3808, 2160, 9, spin, (float *)sink); }, reps);
+        float t0 = timeit([&] { tile_stream<0><<<148, 512>>>((uint8_t *)hostDev, 3808, 2160, 9, spin, (float *)sink); }, reps);
+        float t1 = timeit([&] { tile_stream<1><<<148, 512>>>((uint8_t *)hostDev, 3808, 2160, 9, spin, (float *)sink); }, reps);
+        printf("map tiles at region ends, %5d FMAs per region: to HBM %.3f ms; to pinned host by stores %.3f ms, by the bulk-copy engine %.3f ms\n", spin, tn, t0, t1);
     }
     cudaError_t e = cudaDeviceSynchronize();
     printf("status: %s\n", cudaGetErrorString(e));
