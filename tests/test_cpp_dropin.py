@@ -80,3 +80,34 @@ def test_mgpu_host_strips_effects_and_batch_identical_to_one_gpu(ngpus, rows, co
     if "skipped" in r.stdout:
         pytest.skip(r.stdout.strip())
     assert "all identical" in r.stdout, r.stdout
+
+
+# ---- the per-frame download from a C++ host: pageable, cudaHostRegister'ed and cudaHostAlloc'ed planes -------------------------------
+
+def build_pinned_map():
+    os.makedirs(BUILD, exist_ok=True)
+    out = os.path.join(BUILD, "pinned_map")
+    libdir = os.path.join(ROOT, "realtimedepthdiffusion_b200", "lib")
+    cmd = ["g++", "-std=c++17", "-O1", os.path.join(ROOT, "tests", "cpp", "pinned_map.cpp"), "-I", os.path.join(ROOT, "include"),
+           "-I", os.path.join(CUDA, "include"), "-L", libdir, "-lrtdd", "-L", os.path.join(CUDA, "lib64"), "-lcudart", "-Wl,-rpath," + libdir, "-o", out]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
+    return out
+
+
+def test_pinned_map_links_against_the_c_abi():
+    exe = build_pinned_map()
+    undefined = subprocess.run(["nm", "-u", exe], stdout=subprocess.PIPE, text=True).stdout
+    for fn in ("rtdd_frame_solve_host_annotation", "rtdd_frame_solve_download", "rtdd_frame_paint"):
+        assert re.search(r"\b%s\b" % fn, undefined), fn
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rows,cols,iters", [(540, 960, 1000), (271, 483, 300)])
+def test_pinned_map_same_bytes_whatever_the_host_plane(rows, cols, iters):
+    """rtdd_frame_solve_host_annotation / rtdd_frame_solve_download from C++: the map stored by the last pass into page-locked planes
+    (cudaHostRegister on an ordinary allocation, cudaHostAlloc) equals the staged copy into a pageable one."""
+    exe = build_pinned_map()
+    r = subprocess.run([exe, str(rows), str(cols), str(iters)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=280)
+    assert r.returncode == 0, r.stdout
+    assert "identical" in r.stdout and "MISMATCH" not in r.stdout, r.stdout
