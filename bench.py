@@ -227,10 +227,13 @@ def batch256_1080p(rtdd, dist, rank, world, stream_main):
         c = rtdd.DepthDiffusion(rows, cols)
         st = torch.cuda.Stream()
         c.set_stream(st)
+        if not os.environ.get("RTDD_BATCH_LATENCY_PLAN"):        # (the environment switch exists for the A/B in profiles/)
+            c.set_tuning("plan_throughput", 1)                   # K images share the GPU: pass plans for least SM time, not least latency
         ctxs.append((c, st, torch.empty((rows, cols), dtype=torch.uint8).pin_memory()))
-    for k, (c, st, ho) in enumerate(ctxs):                       # warm-up: graphs, allocations
+    for k, (c, st, ho) in enumerate(ctxs):                       # warm-up: graphs, allocations -- the same calls as the timed loop
         c.frame_set_image(h_bgr[k % len(mine)])
-        c.frame_solve_host_annotation(h_ann[k % len(mine)], 1000, ho)
+        c.frame_solve_host_annotation(h_ann[k % len(mine)], 1000, None)
+        c.frame_read_depth_u8(ho, sync=True)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier(dist)
     ev0.record()

@@ -142,6 +142,8 @@ int rtdd_set_sweep_variant(rtdd_ctx *ctx, int variant, int sweepsPerPass);
  * "fused_prolong": 1 = whole-frame path forms a level's guess inside its set-up kernel, default 0 (no faster);
  * "resident_r1_max_warps": largest one-row-per-warp CTA of the cluster-resident kernel (default 32);
  * "pass_planner": 1 (default) = passes of their own lengths and halos (rtdd_plan_passes), 0 = one length per level (rtdd_plan_blocked);
+ * "plan_throughput": per CONTEXT, 1 = its pass plans minimise total SM time instead of the level's latency -- for contexts that keep
+ *                    the GPU busy together (several images in flight, rtdd_mgpu_batch_solve sets it on its own contexts), default 0;
  * "zero_copy_out": 1 (default) = rtdd_frame_solve_host* let the last level-0 pass store the 8-bit map straight into the caller's
  *                  plane when that is pinned host memory (4-byte aligned base and pitch) and level 0 runs at least 8 sweeps,
  *                  0 = always the staged copy. */
@@ -172,10 +174,11 @@ int rtdd_plan_strip_planes(const int *levelRows, const int *levelCols, int level
 int rtdd_plan_blocked(int rows, int cols, int iterations, int smCount, int *sweepsPerPass, int *clusterForm);
 /* host only: the passes the level driver actually runs (default; rtdd_set_tuning("pass_planner", 0) returns to one length per
  * level): the same cost model, every pass with the halo of its own length, lengths chosen by a small dynamic programme
- * (3840 x 2160 x 31 sweeps: 7, 7, 7, 10).  hostMap = 1: the last pass also stores the 8-bit map into pinned host memory
- * (rtdd_frame_solve_host*) and is made as long as the tiling allows, so that the transfer hides under its sweeps (7, 8, 16).
- * Returns the number of passes (the last pass last), negative on error. */
-int rtdd_plan_passes(int rows, int cols, int iterations, int smCount, int hostMap, int *sweepsOfPass, int capacity, int *clusterForm);
+ * (3840 x 2160 x 31 sweeps: 7, 7, 7, 10).  flags & 1: the last pass also stores the 8-bit map into pinned host memory
+ * (rtdd_frame_solve_host*) and is made as long as the tiling allows, so that the transfer hides under its sweeps (7, 8, 16);
+ * flags & 2: the plan of a context that shares the GPU with others (rtdd_set_tuning "plan_throughput"): least total SM time
+ * instead of least latency.  Returns the number of passes (the last pass last), negative on error. */
+int rtdd_plan_passes(int rows, int cols, int iterations, int smCount, int flags, int *sweepsOfPass, int capacity, int *clusterForm);
 /* The caller's own pass lengths (1..16 sweeps each) for one level of the temporally blocked kernels -- tuning and tests; used
  * whenever the level is solved with exactly their total, npasses = 0 removes them.  Results do not depend on the plan. */
 int rtdd_set_pass_plan(rtdd_ctx *ctx, int level, const int *sweepsOfPass, int npasses);

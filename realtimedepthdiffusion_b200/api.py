@@ -110,11 +110,11 @@ class DepthDiffusion:
         self._ck(lib.rtdd_set_pass_plan(self._h, int(level), arr, n))
 
     @staticmethod
-    def plan_passes(rows, cols, iterations, sm_count=148, host_map=False):
+    def plan_passes(rows, cols, iterations, sm_count=148, host_map=False, throughput=False):
         """(pass lengths, cluster form?) the level driver would use (host only)."""
         arr = (C.c_int * max(iterations, 1))()
         form = C.c_int()
-        n = lib.rtdd_plan_passes(rows, cols, iterations, sm_count, 1 if host_map else 0, arr, max(iterations, 1), C.byref(form))
+        n = lib.rtdd_plan_passes(rows, cols, iterations, sm_count, (1 if host_map else 0) | (2 if throughput else 0), arr, max(iterations, 1), C.byref(form))
         if n < 0:
             raise ValueError("rtdd_plan_passes: %d" % n)
         return list(arr[:n]), bool(form.value)

@@ -208,7 +208,7 @@ int enqueue_sweeps(rtdd_ctx *ctx, cudaStream_t s, int level, int iters, const rt
         } else if (g_passPlanner && ctx->sweepsPerPass <= 0 && form != 0) {
             plan.resize(iters);
             int f2 = form;
-            const int np = rtdd::blocked_plan_passes(L.rows, L.cols, iters, ctx->smCount, (target && target->u8b) ? 1 : 0, plan.data(), iters, &f2);
+            const int np = rtdd::blocked_plan_passes(L.rows, L.cols, iters, ctx->smCount, (target && target->u8b) ? 1 : 0, ctx->planThroughput ? 1 : 0, plan.data(), iters, &f2);
             if (np > 0) { plan.resize(np); form = f2; ownHalo = true; } else plan.clear();
         }
         if (plan.empty())
@@ -438,13 +438,14 @@ int rtdd_plan_blocked(int rows, int cols, int iterations, int smCount, int *swee
     return 0;
 }
 
-// host only: the passes of one level, each with the halo of its own length (see rtdd::blocked_plan_passes); hostMap = 1: the last
-// pass also stores the 8-bit map into pinned host memory and is made as long as the tiling allows
-int rtdd_plan_passes(int rows, int cols, int iterations, int smCount, int hostMap, int *sweepsOfPass, int capacity, int *clusterForm)
+// host only: the passes of one level, each with the halo of its own length (see rtdd::blocked_plan_passes).  flags: 1 = the last
+// pass also stores the 8-bit map into pinned host memory and is made as long as the tiling allows; 2 = plan for throughput (a
+// context of a batch): total SM time instead of the level's latency
+int rtdd_plan_passes(int rows, int cols, int iterations, int smCount, int flags, int *sweepsOfPass, int capacity, int *clusterForm)
 {
-    if (rows < 1 || cols < 1 || iterations < 1 || smCount < 1 || hostMap < 0 || hostMap > 1 || !sweepsOfPass || capacity < 1 || !clusterForm) return RTDD_E_ARG;
+    if (rows < 1 || cols < 1 || iterations < 1 || smCount < 1 || flags < 0 || flags > 3 || !sweepsOfPass || capacity < 1 || !clusterForm) return RTDD_E_ARG;
     int form = 0;
-    const int n = rtdd::blocked_plan_passes(rows, cols, iterations, smCount, hostMap, sweepsOfPass, capacity, &form);
+    const int n = rtdd::blocked_plan_passes(rows, cols, iterations, smCount, flags & 1, (flags >> 1) & 1, sweepsOfPass, capacity, &form);
     if (n <= 0) return RTDD_E_ARG;
     *clusterForm = (form == 3) ? 1 : 0;
     return n;
@@ -677,6 +678,13 @@ int rtdd_set_tuning(rtdd_ctx *ctx, const char *key, int value)
     }
     if (strcmp(key, "pass_planner") == 0 && (value == 0 || value == 1)) {
         g_passPlanner = value;
+        DeviceGuard guard(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+        destroy_graphs(ctx);
+        return 0;
+    }
+    if (strcmp(key, "plan_throughput") == 0 && (value == 0 || value == 1)) {
+        ctx->planThroughput = (value != 0);          // this context only
         DeviceGuard guard(ctx->device);
         cudaStreamSynchronize(ctx->stream);
         destroy_graphs(ctx);

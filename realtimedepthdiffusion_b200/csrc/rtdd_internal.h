@@ -114,6 +114,7 @@ struct rtdd_ctx {
     int dOmegaCap = 0;
     int sweepsPerPass = 0;       // 0 auto
     std::vector<int> passPlan[32];   // per level: the caller's own pass lengths (rtdd_set_pass_plan; empty = the planner's)
+    bool planThroughput = false;     // pass plans minimise total SM time instead of the level's latency (contexts of a batch; "plan_throughput")
     std::map<RtddGraphKey, RtddGraph> graphs;
     std::vector<RtddLevelTiming> captureTiming;   // filled by enqueue_level while a graph is being captured
     unsigned long long launches = 0;
@@ -189,7 +190,7 @@ cudaError_t launch_sweep_blocked(cudaStream_t s, const RtddLevel &L, const float
                                  float *xOut, float *prevOut, OmegaPack om, int T, int nsweeps, float gamma, bool firstSweep, int smCount,
                                  const SweepTarget *target = nullptr, struct HaloPush *push = nullptr, int form = 0);
 void blocked_plan(int rows, int cols, int iters, int smCount, int *T, int *form);
-int blocked_plan_passes(int rows, int cols, int iters, int smCount, int hostMap, int *passes, int capacity, int *form);
+int blocked_plan_passes(int rows, int cols, int iters, int smCount, int hostMap, int throughput, int *passes, int capacity, int *form);
 // staged peer exchange: rows of (x_k, x_{k-1}) between this rank's planes and a staging area, plus the completion flags
 struct HaloRows {
     const float *srcX, *srcP;     // first row to copy of each plane (null: nothing on this side)

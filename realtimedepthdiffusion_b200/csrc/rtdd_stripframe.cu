@@ -267,6 +267,7 @@ void mgpu_worker(rtdd_mgpu *m, int r)
                 rtdd_ctx *c = nullptr;
                 rc = rtdd_create(m->rows, m->cols, m->levels, m->devices[r], &c);
                 if (!rc) rc = rtdd_load_weights(c, m->beta);
+                if (!rc) rc = rtdd_set_tuning(c, "plan_throughput", 1);      // several images in flight: SM time counts, not one image's latency
                 if (c) bc.push_back(c);
             }
             int j = 0;
