@@ -259,9 +259,10 @@ void mgpu_worker(rtdd_mgpu *m, int r)
         case 1: rc = rtdd_strip_frame_solve(ctx, m->iArg); break;
         case 2: rc = rtdd_strip_frame_level0(ctx, m->iArg); break;
         case 3: {
-            // BASELINE configs[3]: image i -> GPU i mod N, every image a full job from host buffers.  Up to 4 images are in flight
-            // per GPU (one context and stream each): the coarse levels keep <= 16 SMs busy, other images' levels fill the rest.
-            const int K = 4;
+            // BASELINE configs[3]: image i -> GPU i mod N, every image a full job from host buffers.  Up to 8 images are in flight
+            // per GPU (one context and stream each): the coarse levels keep <= 16 SMs busy, other images' levels fill the rest
+            // (measured at 1080p, tools/tune_batch.py: 0.89 / 0.79 / 0.70 / 0.66 / 0.67 ms per image with 3 / 4 / 6 / 8 / 12 in flight).
+            const int K = 8;
             std::vector<rtdd_ctx *> &bc = m->batchCtx[r];
             while ((int)bc.size() < K && !rc) {
                 rtdd_ctx *c = nullptr;

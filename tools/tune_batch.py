@@ -11,7 +11,8 @@ sys.path.insert(0, ROOT)
 import realtimedepthdiffusion_b200 as rtdd          # noqa: E402
 from realtimedepthdiffusion_b200 import synth       # noqa: E402
 
-rows, cols, N, K = 1080, 1920, int(sys.argv[1]) if len(sys.argv) > 1 else 96, 6
+rows, cols, N, K = 1080, 1920, int(sys.argv[1]) if len(sys.argv) > 1 else 96, int(sys.argv[2]) if len(sys.argv) > 2 else 6
+ONLY_PLANNERS = len(sys.argv) > 3
 cases = []
 for i in range(8):
     bgr, scribble, edited = synth.synth_case(rows, cols, 2000 + i)
@@ -72,6 +73,8 @@ def rep(t, total):
 
 run("latency planner", lambda c: None)
 run("throughput planner", lambda c: c.set_tuning("plan_throughput", 1))
+if ONLY_PLANNERS:
+    sys.exit(0)
 for tma, nm in ((3, "clusters"), (1, "single CTAs")):
     for t0 in (6, 8, 10, 12):
         run("%s, level 0 in passes of %d" % (nm, t0), plans(rep(t0, 62), None, tma))
