@@ -126,8 +126,10 @@ void pick_variant(const rtdd_ctx *ctx, const RtddLevel &L, int iters, int *varia
         if (t <= 0) {
             // 128x64-tile levels (>= 2^18 pixels): sweeps per pass and form from the cost model fitted to tools/tune_levels.py;
             // smaller levels: 11 (128x32 tiles, measured in round 1)
+            // (a context planned for throughput also takes 128x64 tiles below 2^18 pixels: the flat 128x32 tiles keep 104 x 10 of their
+            // 128 x 32 pixels at 11 sweeps per pass -- fine while the GPU is not full anyway, four times the SM time when it is)
             const long px = (long)L.rows * L.cols;
-            if (px >= (1L << 18)) {
+            if (px >= (1L << 18) || ctx->planThroughput) {
                 int f = 0;
                 rtdd::blocked_plan(L.rows, L.cols, iters, ctx->smCount, &t, &f);
                 if (form) *form = f;
