@@ -12,7 +12,7 @@ import realtimedepthdiffusion_b200 as rtdd          # noqa: E402
 from realtimedepthdiffusion_b200 import synth       # noqa: E402
 
 rows, cols, N, K = 1080, 1920, int(sys.argv[1]) if len(sys.argv) > 1 else 96, int(sys.argv[2]) if len(sys.argv) > 2 else 6
-ONLY_PLANNERS = len(sys.argv) > 3
+ONLY_PLANNERS = len(sys.argv) > 3 and sys.argv[3] == "planners"
 cases = []
 for i in range(8):
     bgr, scribble, edited = synth.synth_case(rows, cols, 2000 + i)
@@ -74,6 +74,21 @@ def rep(t, total):
 run("latency planner", lambda c: None)
 run("throughput planner", lambda c: c.set_tuning("plan_throughput", 1))
 if ONLY_PLANNERS:
+    sys.exit(0)
+
+
+def level2(plan, tma):
+    def f(c):
+        c.set_tuning("plan_throughput", 1)
+        c.set_tuning("blocked_tma", tma)
+        c.set_pass_plan(2, plan)
+    return f
+
+
+if len(sys.argv) > 3 and sys.argv[3] == "level2":
+    for tma, nm in ((3, "clusters"), (1, "single CTAs")):
+        for t2 in (6, 8, 10, 12, 16):
+            run("throughput plans; level 2 (480x270) %s, passes of %d" % (nm, t2), level2(rep(t2, 250), tma))
     sys.exit(0)
 for tma, nm in ((3, "clusters"), (1, "single CTAs")):
     for t0 in (6, 8, 10, 12):
