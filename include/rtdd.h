@@ -177,7 +177,9 @@ int rtdd_plan_blocked(int rows, int cols, int iterations, int smCount, int *swee
  * (3840 x 2160 x 31 sweeps: 7, 7, 7, 10).  flags & 1: the last pass also stores the 8-bit map into pinned host memory
  * (rtdd_frame_solve_host*) and is made as long as the tiling allows, so that the transfer hides under its sweeps (7, 8, 16);
  * flags & 2: the plan of a context that shares the GPU with others (rtdd_set_tuning "plan_throughput"): least total SM time
- * instead of least latency.  Returns the number of passes (the last pass last), negative on error. */
+ * instead of least latency.  *clusterForm: 1 = clusters of two CTAs on 128 x 128 regions, 0 = single CTAs on 128 x 64 regions,
+ * 2 = single CTAs on 128 x 32 regions (levels below 2^18 pixels only).  Returns the number of passes (the last pass last),
+ * negative on error. */
 int rtdd_plan_passes(int rows, int cols, int iterations, int smCount, int flags, int *sweepsOfPass, int capacity, int *clusterForm);
 /* The caller's own pass lengths (1..16 sweeps each) for one level of the temporally blocked kernels -- tuning and tests; used
  * whenever the level is solved with exactly their total, npasses = 0 removes them.  Results do not depend on the plan. */

@@ -111,13 +111,14 @@ class DepthDiffusion:
 
     @staticmethod
     def plan_passes(rows, cols, iterations, sm_count=148, host_map=False, throughput=False):
-        """(pass lengths, cluster form?) the level driver would use (host only)."""
+        """(pass lengths, form) the level driver would use (host only); form: 1 = clusters of two CTAs on 128x128 regions,
+        0 = single CTAs on 128x64 regions, 2 = single CTAs on 128x32 regions."""
         arr = (C.c_int * max(iterations, 1))()
         form = C.c_int()
         n = lib.rtdd_plan_passes(rows, cols, iterations, sm_count, (1 if host_map else 0) | (2 if throughput else 0), arr, max(iterations, 1), C.byref(form))
         if n < 0:
             raise ValueError("rtdd_plan_passes: %d" % n)
-        return list(arr[:n]), bool(form.value)
+        return list(arr[:n]), int(form.value)
 
     # -- GPUSolver -------------------------------------------------------------
     def load_weights(self, beta):

@@ -135,6 +135,7 @@ void pick_variant(const rtdd_ctx *ctx, const RtddLevel &L, int iters, int *varia
                 if (form) *form = f;
             } else {
                 t = 11;
+                if (form) *form = 2;         // 128x32 tiles; the pass planner may still move the level to another form
             }
         }
         if (t > RTDD_MAX_T) t = RTDD_MAX_T;
@@ -449,7 +450,7 @@ int rtdd_plan_passes(int rows, int cols, int iterations, int smCount, int flags,
     int form = 0;
     const int n = rtdd::blocked_plan_passes(rows, cols, iterations, smCount, flags & 1, (flags >> 1) & 1, sweepsOfPass, capacity, &form);
     if (n <= 0) return RTDD_E_ARG;
-    *clusterForm = (form == 3) ? 1 : 0;
+    *clusterForm = (form == 3) ? 1 : (form == 2) ? 2 : 0;
     return n;
 }
 
