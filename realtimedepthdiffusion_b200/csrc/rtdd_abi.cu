@@ -251,7 +251,8 @@ struct LevelArgs {
 
 // Opt-in (rtdd_set_tuning("fused_prolong", 1)): bit-identical and tested, but measured no faster than the three separate
 // kernels inside the frame graph (4K 1.9025 vs 1.8945 ms, 8K UHD 3.081 vs 3.065 ms, 1080p 1.306 vs 1.307 ms): with
-// programmatic dependent launch the small kernels already overlap, and the 66 MB saved at 4K are ~1 % of a frame.
+// programmatic dependent launch the small kernels already overlap, and the 66 MB saved at 4K are ~1 % of a frame.  Re-measured with
+// the final round-2 kernels: 1.751 against 1.740 ms.
 static int g_fusedProlong = 0;
 
 // One level on stream `s`: edge-weight pass, sweeps, result into the caller's depth plane.  `capturing` selects
