@@ -7,10 +7,14 @@
   step     one whole solve frame (main.cpp:232-295: annotation restriction, Dirichlet injection,
            per level edge-weight pass + sweeps + copy back, depth prolongation, 8-bit quantise)
   value    device-resident (annotations already in HBM), CUDA events, max over ranks
-  e2e      the same frame through rtdd_frame_solve_host with HOST buffers: scribble + edited
-           uploaded from pinned memory and the 8-bit depth map downloaded inside the timed region
-  N > 1    batch data parallelism (configs[3]): every rank solves its own image, no collective
-           on the data path => weak scaling
+  e2e      the same frame through rtdd_frame_solve_host_annotation with HOST buffers: the annotation
+           plane (1 B/px, main.cpp:160-170's format) uploaded from pinned memory and the 8-bit depth
+           map delivered into pinned memory inside the timed region (the last sweep pass stores it
+           there itself); e2e.three_plane_upload = rtdd_frame_solve_host with main.cpp's own
+           scribble + 3-channel edited planes
+  N > 1    batch data parallelism: every rank solves its own 4K image, no collective on the data
+           path => weak scaling; plus, at every N, the records batch256_1080p (configs[3] as written)
+           and strips16k (configs[4]: one 16384^2 image in row strips, strong scaling)
 
 --impl reference runs the reference's OWN kernels (oracle/_ref/libref.so, compiled unmodified from
 /root/reference/src/*.cu) through the reference's own functions on the same workload.  The
